@@ -1,0 +1,156 @@
+/* mpb200.h -- C ABI of the B200-native greedy matching-pursuit engine.
+ *
+ * The reference (JohnVinyard/matching-pursuit) is pure Python/PyTorch and has
+ * no FFI; the boundary it offers is a set of Python callables (SURVEY.md
+ * section 8b).  This header is the C-level seam those callables are re-hosted
+ * on: every entry point names the reference interface it replaces (paths are
+ * relative to the reference tree).  Signatures carry plain pointers and sizes
+ * only -- no torch types.  Unless a function says "host", every pointer is a
+ * DEVICE pointer to contiguous memory, work is enqueued on `stream` (a
+ * cudaStream_t passed as void*; NULL = legacy default stream) and the call
+ * returns without synchronising.  All arithmetic is fp32; indices are int32
+ * (positions < 2^31, atoms < 2^31).
+ *
+ * Return value: 0 on success, a negative MPB200_E* code otherwise;
+ * mpb200_last_error() gives the message for the calling thread.
+ */
+#ifndef MPB200_H
+#define MPB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPB200_VERSION 100
+
+#define MPB200_OK 0
+#define MPB200_EINVAL (-1)   /* bad argument / unsupported shape */
+#define MPB200_ECUDA (-2)    /* CUDA runtime error */
+#define MPB200_ENOMEM (-3)   /* device allocation failed */
+#define MPB200_ESTATE (-4)   /* call sequence error (no dictionary set, ...) */
+
+/* How the correlation map is kept up to date after the first full pass. */
+#define MPB200_MODE_AUTO 0        /* GRAM when the table fits the budget, else RECORRELATE */
+#define MPB200_MODE_RECORRELATE 1 /* re-correlate the +-A window of each winner by FFT; only block maxima are resident */
+#define MPB200_MODE_GRAM 2        /* resident map, updated from a precomputed atom cross-correlation table */
+#define MPB200_MODE_FULL 3        /* recompute the whole map every step (the reference's schedule) */
+
+typedef struct mpb200_plan* mpb200_plan_t;
+
+typedef struct mpb200_plan_info {
+    int32_t n_atoms, atom_size, n_samples, max_batch;
+    int32_t mode;            /* resolved mode (never AUTO) */
+    int32_t fft_size;        /* M: window FFT length */
+    int32_t block;           /* positions per block-max entry */
+    int32_t n_blocks;        /* ceil(n_samples / block) */
+    int32_t atom_lo, atom_hi;/* atoms owned by this plan (atom sharding) */
+    int32_t reserved0, reserved1;
+    uint64_t device_bytes;   /* device memory owned by the plan */
+    uint64_t gram_bytes;     /* of which: Gram table */
+} mpb200_plan_info;
+
+/* One selection record, 16 bytes; what atom-sharded ranks exchange per step. */
+typedef struct mpb200_best {
+    float value;
+    int32_t atom;     /* global atom index */
+    int32_t position;
+    int32_t pad;
+} mpb200_best;
+
+int mpb200_version(void);
+const char* mpb200_last_error(void);
+
+/* Plan: sizes workspaces for signals of n_samples, batches up to max_batch and
+ * a dictionary of n_atoms x atom_size of which this plan owns atoms
+ * [atom_lo, atom_hi) (pass 0, n_atoms for no sharding).  gram_budget_bytes
+ * bounds the Gram table in AUTO mode (0 = default 40% of free memory).
+ * No reference counterpart: the reference re-derives everything per call
+ * (modules/matchingpursuit.py:254-259). */
+int mpb200_plan_create(mpb200_plan_t* plan, int n_atoms, int atom_size, int n_samples, int max_batch,
+                       int mode, int atom_lo, int atom_hi, uint64_t gram_budget_bytes);
+int mpb200_plan_destroy(mpb200_plan_t plan);
+int mpb200_plan_info_get(mpb200_plan_t plan, mpb200_plan_info* info);
+
+/* Dictionary: d is (n_atoms, atom_size) row-major.  The plan keeps
+ * x / (||x||_2 + 1e-8) per row -- modules/normalization.py:4-6, applied by the
+ * reference at every entry (modules/matchingpursuit.py:254) -- and derives the
+ * atom-pair spectra (and the Gram table in GRAM mode).  The caller's buffer is
+ * not modified and may be freed once `stream` has passed this call. */
+int mpb200_plan_set_dictionary(mpb200_plan_t plan, const float* d, void* stream);
+/* Copy of the normalised dictionary (n_atoms, atom_size). */
+int mpb200_plan_get_unit_dictionary(mpb200_plan_t plan, float* out, void* stream);
+
+/* Greedy pursuit -- replaces the loop of modules/matchingpursuit.py:269-328
+ * (sparse_code) and :87-120 (sparse_feature_map).
+ *   signal        (batch, n_samples), not modified
+ *   residual_out  (batch, n_samples), receives signal - sum of selected atoms
+ *   atom_out/pos_out/val_out  (batch, n_steps) row-major: step s of signal b at [b*n_steps + s]
+ * Exactly n_steps events per signal (no early stop); value is the signed
+ * correlation at the winner; ties go to the lowest (atom, position). */
+int mpb200_sparse_code(mpb200_plan_t plan, const float* signal, int batch, int n_steps,
+                       float* residual_out, int32_t* atom_out, int32_t* pos_out, float* val_out,
+                       void* stream);
+/* Same with HOST buffers (pinned or pageable): copies in, runs, copies out and
+ * synchronises `stream` before returning.  This is the end-to-end entry the
+ * Python drop-ins use for CPU tensors. */
+int mpb200_sparse_code_host(mpb200_plan_t plan, const float* signal_host, int batch, int n_steps,
+                            float* residual_out_host, int32_t* atom_out_host, int32_t* pos_out_host,
+                            float* val_out_host, void* stream);
+
+/* Dense correlation map fm[b,k,t] = sum_i pad(signal)[b,t+i] * d_unit[k,i],
+ * (batch, n_owned_atoms, n_samples) -- replaces F.pad+F.conv1d+crop at
+ * modules/matchingpursuit.py:275-277, modules/conv.py:4-9 (torch_conv) and
+ * the full-product branch of modules/conv.py:11-53 (fft_convolve); it is also
+ * the `compute_feature_map` callback seam (modules/matchingpursuit.py:272-273). */
+int mpb200_correlate(mpb200_plan_t plan, const float* signal, int batch, float* fm_out, void* stream);
+
+/* Step-wise interface (atom sharding across GPUs, and callers that need to
+ * look at every step):
+ *   begin       load signals, run the first full pass
+ *   local_best  this plan's best (value, global atom, position) per signal -> best[batch]
+ *   apply       subtract winner[b] (an atom this plan may not own: the whole
+ *               dictionary is replicated) from the residual and refresh this
+ *               plan's map/block maxima in the +-A window
+ *   residual    copy out the current residual
+ * Between local_best and apply the caller reduces the records across ranks
+ * (max value, then lowest atom, then lowest position). */
+int mpb200_begin(mpb200_plan_t plan, const float* signal, int batch, void* stream);
+int mpb200_local_best(mpb200_plan_t plan, mpb200_best* best, void* stream);
+int mpb200_apply(mpb200_plan_t plan, const mpb200_best* winner, void* stream);
+int mpb200_residual(mpb200_plan_t plan, float* residual_out, void* stream);
+/* Reduce `n_ranks` candidate lists (rank-major: cand[r*batch + b]) to the
+ * global winner per signal with the reference tie-break; used after an
+ * all-gather of mpb200_local_best records. */
+int mpb200_reduce_best(const mpb200_best* cand, int n_ranks, int batch, mpb200_best* winner, void* stream);
+
+/* Decode: out[b, pos : pos+atom_size] += val * d_unit[atom], truncated at the
+ * right edge -- replaces scatter_segments, modules/matchingpursuit.py:20-58
+ * (single-channel branch :48).  out is (batch, n_samples) and is accumulated
+ * into (zero it first for a fresh decode).  Events: n_events entries of
+ * (atom, batch index, position, value). */
+int mpb200_scatter_add(float* out, int batch, int n_samples, const float* d_unit, int n_atoms, int atom_size,
+                       const int32_t* atom, const int32_t* batch_index, const int32_t* pos, const float* val,
+                       int n_events, void* stream);
+/* scaled[e, :] = val[e] * d_unit[atom[e], :]  -- the `a` member of the
+ * reference's event tuples (modules/matchingpursuit.py:305, 315). */
+int mpb200_gather_atoms(float* scaled, const float* d_unit, int n_atoms, int atom_size,
+                        const int32_t* atom, const float* val, int n_events, void* stream);
+
+/* y = x / (||x||_2 + eps) per row -- modules/normalization.py:4-6. */
+int mpb200_unit_norm(const float* x, float* y, int rows, int cols, float eps, void* stream);
+
+/* out[r, :n] = first n samples of the linear convolution (conjugate_b = 0) or
+ * correlation (conjugate_b = 1) of a[r % rows_a, :n] with b[r % rows_b, :n],
+ * both zero-padded to 2n -- replaces modules/fft.py:23-35 and
+ * modules/transfer.py:548-569 for two operands (rows = max(rows_a, rows_b);
+ * broadcasting over leading dimensions is done by the caller's row indexing). */
+int mpb200_fft_convolve(const float* a, int rows_a, const float* b, int rows_b, int n, int conjugate_b,
+                        float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPB200_H */

@@ -1,0 +1,107 @@
+"""ctypes binding of ``libmpb200.so`` (the C ABI declared in ``include/mpb200.h``).
+
+There is no CPU path: if the library has not been built, or no CUDA device is
+present, every entry point of this package raises.  Build with
+``python -c "import __graft_entry__ as g; g.build()"`` (nvcc, sm_100a).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_PATH = os.path.join(HERE, "libmpb200.so")
+SOURCES = ["mpb200.cu", "fftconv.cu"]
+HEADERS = ["kernels.cuh", "fft_core.cuh", "types.h", "plan.h"]
+
+MODE_AUTO, MODE_RECORRELATE, MODE_GRAM, MODE_FULL = 0, 1, 2, 3
+MODES = {"auto": MODE_AUTO, "recorrelate": MODE_RECORRELATE, "gram": MODE_GRAM, "full": MODE_FULL}
+MODE_NAMES = {v: k for k, v in MODES.items()}
+
+
+class PlanInfo(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "n_atoms", "atom_size", "n_samples", "max_batch", "mode", "fft_size", "block", "n_blocks",
+        "atom_lo", "atom_hi", "reserved0", "reserved1")] + [("device_bytes", C.c_uint64), ("gram_bytes", C.c_uint64)]
+
+
+class MpbError(RuntimeError):
+    pass
+
+
+def nvcc_command(out_path: str = LIB_PATH, extra=()):
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+            "-Xcompiler", "-fPIC", "-shared", *extra, "-o", out_path] + [os.path.join(CSRC, s) for s in SOURCES]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    built = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(os.path.dirname(HERE), "include", "mpb200.h")]
+    return any(os.path.getmtime(d) > built for d in deps if os.path.exists(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the library in-tree for sm_100a (cross-compiles without a GPU)."""
+    if force or needs_build():
+        cmd = nvcc_command()
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+_lib = None
+
+_p = C.c_void_p
+_i = C.c_int
+_SIGNATURES = {
+    "mpb200_version": (C.c_int, []),
+    "mpb200_last_error": (C.c_char_p, []),
+    "mpb200_plan_create": (_i, [C.POINTER(_p), _i, _i, _i, _i, _i, _i, _i, C.c_uint64]),
+    "mpb200_plan_destroy": (_i, [_p]),
+    "mpb200_plan_info_get": (_i, [_p, C.POINTER(PlanInfo)]),
+    "mpb200_plan_set_dictionary": (_i, [_p, _p, _p]),
+    "mpb200_plan_get_unit_dictionary": (_i, [_p, _p, _p]),
+    "mpb200_sparse_code": (_i, [_p, _p, _i, _i, _p, _p, _p, _p, _p]),
+    "mpb200_sparse_code_host": (_i, [_p, _p, _i, _i, _p, _p, _p, _p, _p]),
+    "mpb200_correlate": (_i, [_p, _p, _i, _p, _p]),
+    "mpb200_begin": (_i, [_p, _p, _i, _p]),
+    "mpb200_local_best": (_i, [_p, _p, _p]),
+    "mpb200_apply": (_i, [_p, _p, _p]),
+    "mpb200_residual": (_i, [_p, _p, _p]),
+    "mpb200_reduce_best": (_i, [_p, _i, _i, _p, _p]),
+    "mpb200_scatter_add": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _i, _p]),
+    "mpb200_scatter_rows": (_i, [_p, _i, _i, _p, _i, _p, _p, _i, _p]),
+    "mpb200_gather_atoms": (_i, [_p, _p, _i, _i, _p, _p, _i, _p]),
+    "mpb200_unit_norm": (_i, [_p, _p, _i, _i, C.c_float, _p]),
+    "mpb200_fft_convolve": (_i, [_p, _i, _p, _i, _i, _i, _p, _p]),
+}
+EXPORTED = tuple(_SIGNATURES)
+
+
+def lib():
+    """The loaded library; raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MpbError(
+                f"{LIB_PATH} is missing: the CUDA library has not been built and this package has no "
+                "CPU path.  Run: python -c \"import __graft_entry__ as g; g.build()\"")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().mpb200_last_error().decode("utf-8", "replace")
+        raise MpbError(f"{what or 'mpb200 call'} failed ({rc}): {msg}")

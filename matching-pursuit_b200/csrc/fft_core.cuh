@@ -1,0 +1,260 @@
+// fft_core.cuh -- register-radix / shared-memory three-pass FFT building blocks.
+//
+// Everything here is __host__ __device__ so that the index arithmetic and the
+// butterflies can be exercised on the CPU (tests/test_fft_core_host.py compiles
+// csrc/host_emulation.cpp with g++ and walks the "threads" of a block
+// sequentially, phase by phase) before any GPU minute is spent.
+//
+// Transform:   out[m] = sum_j in[j] * exp(DIR * 2*pi*i * j*m / M),   M = 256 * R1,
+// R1 in {1,2,4,8,16,32}.  Decomposition j = j1*256 + x*16 + j3,
+// m = m1 + R1*m2 + 16*R1*m3:
+//   pass 1  radix-R1 over j1  (-> m1),  twiddle w_M^{c*m1},   c = x*16 + j3
+//   pass 2  radix-16 over x   (-> m2),  twiddle w_256^{j3*m2}
+//   pass 3  radix-16 over j3  (-> m3)
+// Input and output are both in natural order; the two exchanges between the
+// passes go through one shared-memory buffer with a bank-conflict-free layout
+// (see BlockFft::addr).
+#pragma once
+#include <cstdint>
+#include <type_traits>
+
+#if defined(__CUDACC__)
+#define MPB_HD __host__ __device__ __forceinline__
+#else
+#define MPB_HD inline
+#endif
+
+namespace mpb {
+
+template <typename T>
+struct cpx {
+    T x, y;
+};
+
+template <typename T> MPB_HD cpx<T> operator+(cpx<T> a, cpx<T> b) { return {a.x + b.x, a.y + b.y}; }
+template <typename T> MPB_HD cpx<T> operator-(cpx<T> a, cpx<T> b) { return {a.x - b.x, a.y - b.y}; }
+template <typename T> MPB_HD cpx<T> cmul(cpx<T> a, cpx<T> b) {
+    return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+}
+template <typename T> MPB_HD cpx<T> cconj(cpx<T> a) { return {a.x, -a.y}; }
+
+template <int B, int E, typename F>
+MPB_HD void static_for(F&& f) {
+    if constexpr (B < E) {
+        f(std::integral_constant<int, B>{});
+        static_for<B + 1, E>(f);
+    }
+}
+
+// cos(2*pi*m/32), m = 0..8
+template <int M32>
+struct Cos32 {
+    static constexpr double value =
+        M32 == 0 ? 1.0 :
+        M32 == 1 ? 0.9807852804032304491261822 :
+        M32 == 2 ? 0.9238795325112867561281832 :
+        M32 == 3 ? 0.8314696123025452370787884 :
+        M32 == 4 ? 0.7071067811865475244008444 :
+        M32 == 5 ? 0.5555702330196022247428308 :
+        M32 == 6 ? 0.3826834323650897717284600 :
+        M32 == 7 ? 0.1950903220161282678482849 : 0.0;
+};
+
+// v * exp(DIR * 2*pi*i * NUM / DEN) with NUM, DEN compile-time; DEN | 32.
+template <int DIR, int DEN, int NUM, typename T>
+MPB_HD cpx<T> tw_const(cpx<T> v) {
+    constexpr int q = (((NUM % DEN) + DEN) % DEN) * (32 / DEN);  // angle in 32nds of a turn, 0..31
+    if constexpr (q == 0) {
+        return v;
+    } else if constexpr (q == 16) {
+        return {-v.x, -v.y};
+    } else if constexpr (q == 8) {           // * (DIR * i)
+        if constexpr (DIR > 0) return {-v.y, v.x};
+        else return {v.y, -v.x};
+    } else if constexpr (q == 24) {          // * (-DIR * i)
+        if constexpr (DIR > 0) return {v.y, -v.x};
+        else return {-v.y, v.x};
+    } else {
+        // reduce to first quadrant: angle = quad*8 + r, r in 1..7
+        constexpr int quad = q / 8, r = q % 8;
+        constexpr T c = (T)Cos32<r>::value;
+        constexpr T s = (T)Cos32<8 - r>::value;   // sin(2 pi r/32) = cos(2 pi (8-r)/32)
+        constexpr T ss = DIR > 0 ? s : -s;
+        cpx<T> t;
+        if constexpr (r == 4) {
+            // 45 degrees: c == s, two multiplies instead of four
+            constexpr T h = (T)Cos32<4>::value;
+            if constexpr (DIR > 0) t = {(v.x - v.y) * h, (v.x + v.y) * h};
+            else t = {(v.x + v.y) * h, (v.y - v.x) * h};
+        } else {
+            t = {v.x * c - v.y * ss, v.x * ss + v.y * c};
+        }
+        // multiply by (DIR*i)^quad
+        if constexpr (quad == 0) return t;
+        else if constexpr (quad == 2) return {-t.x, -t.y};
+        else if constexpr ((quad == 1) == (DIR > 0)) return {-t.y, t.x};
+        else return {t.y, -t.x};
+    }
+}
+
+// In-register DFT of R points, natural order in and out:
+//   v[k] <- sum_n v[n] * exp(DIR * 2*pi*i * n*k / R)
+template <int R, int DIR, typename T>
+struct Dft {
+    static MPB_HD void run(cpx<T>* v) {
+        static_assert(R == 8 || R == 16 || R == 32, "radix");
+        constexpr int R1 = 4, R2 = R / 4;
+        cpx<T> tmp[R];
+        static_for<0, R2>([&](auto n2c) {
+            constexpr int n2 = decltype(n2c)::value;
+            cpx<T> col[R1];
+            static_for<0, R1>([&](auto n1c) {
+                constexpr int n1 = decltype(n1c)::value;
+                col[n1] = v[n1 * R2 + n2];
+            });
+            Dft<R1, DIR, T>::run(col);
+            static_for<0, R1>([&](auto k1c) {
+                constexpr int k1 = decltype(k1c)::value;
+                tmp[k1 * R2 + n2] = tw_const<DIR, R, n2 * k1, T>(col[k1]);
+            });
+        });
+        static_for<0, R1>([&](auto k1c) {
+            constexpr int k1 = decltype(k1c)::value;
+            cpx<T> row[R2];
+            static_for<0, R2>([&](auto n2c) {
+                constexpr int n2 = decltype(n2c)::value;
+                row[n2] = tmp[k1 * R2 + n2];
+            });
+            Dft<R2, DIR, T>::run(row);
+            static_for<0, R2>([&](auto k2c) {
+                constexpr int k2 = decltype(k2c)::value;
+                v[k1 + R1 * k2] = row[k2];
+            });
+        });
+    }
+};
+template <int DIR, typename T>
+struct Dft<1, DIR, T> {
+    static MPB_HD void run(cpx<T>*) {}
+};
+template <int DIR, typename T>
+struct Dft<2, DIR, T> {
+    static MPB_HD void run(cpx<T>* v) {
+        cpx<T> a = v[0], b = v[1];
+        v[0] = a + b;
+        v[1] = a - b;
+    }
+};
+template <int DIR, typename T>
+struct Dft<4, DIR, T> {
+    static MPB_HD void run(cpx<T>* v) {
+        cpx<T> t0 = v[0] + v[2], t1 = v[0] - v[2], t2 = v[1] + v[3];
+        cpx<T> t3 = tw_const<DIR, 4, 1, T>(v[1] - v[3]);
+        v[0] = t0 + t2;
+        v[2] = t0 - t2;
+        v[1] = t1 + t3;
+        v[3] = t1 - t3;
+    }
+};
+
+// Three-pass block FFT of M = 256*R1 points carried by T = M/E threads, each
+// holding E = max(R1,16) complex values in registers.
+//
+// Shared buffer layout between the passes, logical index (m1, x, j3) with
+// m1 < R1, x < 16, j3 < 16:
+//      addr = x*XS + j3*S + m1,   S = R1|1 (odd),  XS = 16*S + (R1 < 16 ? R1 : 0)
+//  * pass-1 store / pass-2 load+store: one instruction has fixed (m1 or x), the
+//    16 lanes of a half-warp walk j3 -> stride S (odd) -> 16 distinct 8-byte banks
+//  * pass-3 load: fixed j3, lanes walk mu = m1 + R1*m2 -> consecutive addresses
+//    inside one x, and the XS padding keeps consecutive x on distinct banks.
+template <int M_, typename Real>
+struct BlockFft {
+    using C = cpx<Real>;
+    static constexpr int M = M_;
+    static constexpr int R1 = M / 256;
+    static_assert(R1 == 1 || R1 == 2 || R1 == 4 || R1 == 8 || R1 == 16 || R1 == 32, "M must be 256..8192, power of 2");
+    static constexpr int E = R1 > 16 ? R1 : 16;     // complex values per thread
+    static constexpr int T = M / E;                 // threads per transform
+    static constexpr int NB1 = E / R1;              // pass-1 columns per thread
+    static constexpr int NB2 = E / 16;              // pass-2 / pass-3 butterflies per thread
+    static constexpr int S = R1 | 1;
+    static constexpr int XS = 16 * S + (R1 < 16 ? R1 : 0);
+    static constexpr int SMEM_CPX = 16 * XS;        // >= M
+    static constexpr int TW1 = M;                   // tw1[m1*256 + c] = exp(+2 pi i c m1 / M)
+    static constexpr int TW2 = 256;                 // tw2[m2*16 + j3] = exp(+2 pi i j3 m2 / 256)
+
+    static MPB_HD int addr(int m1, int x, int j3) { return x * XS + j3 * S + m1; }
+
+    // Which input element lives in register slot e of thread tl before pass 1.
+    static MPB_HD int in_index(int tl, int e) {
+        int u = e / R1, j1 = e % R1;
+        return j1 * 256 + (tl + T * u);
+    }
+    // Which output element lives in register slot e of thread tl after pass 3.
+    static MPB_HD int out_index(int tl, int e) {
+        int u = e / 16, m3 = e % 16;
+        return (tl + T * u) + (M / 16) * m3;
+    }
+
+    // r[u*R1 + j1] holds in[j1*256 + c], c = tl + T*u.
+    template <int DIR>
+    static MPB_HD void pass1(C* r, int tl, C* sm, const C* __restrict__ tw1) {
+        static_for<0, NB1>([&](auto uc) {
+            constexpr int u = decltype(uc)::value;
+            const int c = tl + T * u;
+            Dft<R1, DIR, Real>::run(r + u * R1);
+            const int x = c >> 4, j3 = c & 15;
+            static_for<0, R1>([&](auto m1c) {
+                constexpr int m1 = decltype(m1c)::value;
+                C v = r[u * R1 + m1];
+                if constexpr (m1 > 0) {
+                    C w = tw1[m1 * 256 + c];
+                    if constexpr (DIR < 0) w.y = -w.y;
+                    v = cmul(v, w);
+                }
+                sm[addr(m1, x, j3)] = v;
+            });
+        });
+    }
+
+    template <int DIR>
+    static MPB_HD void pass2(C* r, int tl, C* sm, const C* __restrict__ tw2) {
+        static_for<0, NB2>([&](auto uc) {
+            constexpr int u = decltype(uc)::value;
+            const int beta = tl + T * u;
+            const int j3 = beta & 15, m1 = beta >> 4;
+            static_for<0, 16>([&](auto xc) {
+                constexpr int x = decltype(xc)::value;
+                r[u * 16 + x] = sm[addr(m1, x, j3)];
+            });
+            Dft<16, DIR, Real>::run(r + u * 16);
+            static_for<0, 16>([&](auto m2c) {
+                constexpr int m2 = decltype(m2c)::value;
+                C v = r[u * 16 + m2];
+                if constexpr (m2 > 0) {
+                    C w = tw2[m2 * 16 + j3];
+                    if constexpr (DIR < 0) w.y = -w.y;
+                    v = cmul(v, w);
+                }
+                sm[addr(m1, m2, j3)] = v;
+            });
+        });
+    }
+
+    // afterwards r[u*16 + m3] = out[(tl + T*u) + (M/16)*m3]
+    template <int DIR>
+    static MPB_HD void pass3(C* r, int tl, const C* sm) {
+        static_for<0, NB2>([&](auto uc) {
+            constexpr int u = decltype(uc)::value;
+            const int mu = tl + T * u;
+            const int m1 = mu % R1, m2 = mu / R1;
+            static_for<0, 16>([&](auto jc) {
+                constexpr int j3 = decltype(jc)::value;
+                r[u * 16 + j3] = sm[addr(m1, m2, j3)];
+            });
+            Dft<16, DIR, Real>::run(r + u * 16);
+        });
+    }
+};
+
+}  // namespace mpb

@@ -1,0 +1,526 @@
+// kernels.cuh -- device kernels of the matching-pursuit engine (sm_100a).
+//
+// Data layout in HBM (all fp32 / int32, row-major):
+//   residual   (B, N)
+//   dict       (K, A)             unit-normed atoms (whole dictionary, replicated)
+//   pairspec   (P, M) complex     P = ceil(K_owned/2); spectrum of the complex
+//                                 sequence d[2q] + i*d[2q+1] with the inverse
+//                                 kernel, scaled 1/M: one complex IFFT of
+//                                 X_window * pairspec[q] yields the correlation
+//                                 of the window with atom 2q (real part) and
+//                                 atom 2q+1 (imaginary part)
+//   winspec    (W, M) complex     forward FFT of residual windows
+//   bm_val/bm_pos (B, K_owned, NB) max / argmax of each `blk` consecutive positions
+//   row_val/row_pos (B, K_owned)   max / argmax of each map row
+#pragma once
+#include <cuda_runtime.h>
+#include <cfloat>
+#include <climits>
+#include "fft_core.cuh"
+#include "types.h"
+
+namespace mpb {
+
+constexpr int MODE_BLOCKMAX = 1;
+constexpr int MODE_ROWMAX = 2;
+constexpr int MODE_DENSE = 4;
+
+__device__ __forceinline__ C32 ld_stream(const C32* p) {
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return {v.x, v.y};
+}
+
+// (value, index) ordering of torch.max over a flattened map: larger value
+// wins, equal values go to the lower index.
+__device__ __forceinline__ void take_better(float& v, int& i, float ov, int oi) {
+    if (ov > v || (ov == v && oi < i)) {
+        v = ov;
+        i = oi;
+    }
+}
+__device__ __forceinline__ void warp_argmax(float& v, int& i) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, v, off);
+        int oi = __shfl_xor_sync(0xffffffffu, i, off);
+        take_better(v, i, ov, oi);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// y = x / (||x|| + eps) per row (modules/normalization.py:4-6). One warp per row.
+// ---------------------------------------------------------------------------
+__global__ void k_unit_norm(const float* __restrict__ x, float* __restrict__ y, int rows, int cols, float eps) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* xr = x + (size_t)row * cols;
+    double acc = 0.0;
+    for (int i = lane; i < cols; i += 32) {
+        double v = xr[i];
+        acc += v * v;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    const float denom = __fadd_rn((float)sqrt(acc), eps);
+    for (int i = lane; i < cols; i += 32) y[(size_t)row * cols + i] = __fdiv_rn(xr[i], denom);
+}
+
+// ---------------------------------------------------------------------------
+// Spectra of atom pairs.  pair q of this plan = atoms (atom_lo + 2q, atom_lo + 2q + 1).
+// ---------------------------------------------------------------------------
+template <int M, typename Real>
+__global__ void __launch_bounds__(BlockFft<M, Real>::T)
+k_pair_spectra(const float* __restrict__ dict, int A, int atom_lo, int atom_hi,
+               const cpx<Real>* __restrict__ tw1, const cpx<Real>* __restrict__ tw2, C32* __restrict__ pairspec) {
+    using F = BlockFft<M, Real>;
+    using C = cpx<Real>;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    C* sm = reinterpret_cast<C*>(smraw);
+    C* stw2 = sm + F::SMEM_CPX;
+    const int tl = threadIdx.x, q = blockIdx.x;
+    for (int i = tl; i < 256; i += F::T) stw2[i] = tw2[i];
+    const int k0 = atom_lo + 2 * q, k1 = k0 + 1;
+    const float* d0 = dict + (size_t)k0 * A;
+    const float* d1 = dict + (size_t)k1 * A;
+    C r[F::E];
+#pragma unroll
+    for (int e = 0; e < F::E; ++e) {
+        const int j = F::in_index(tl, e);
+        Real re = (j < A) ? (Real)d0[j] : (Real)0;
+        Real im = (j < A && k1 < atom_hi) ? (Real)d1[j] : (Real)0;
+        r[e] = {re, im};
+    }
+    __syncthreads();
+    F::template pass1<1>(r, tl, sm, tw1);
+    __syncthreads();
+    F::template pass2<1>(r, tl, sm, stw2);
+    __syncthreads();
+    F::template pass3<1>(r, tl, sm);
+    const Real scale = (Real)1 / (Real)M;
+#pragma unroll
+    for (int e = 0; e < F::E; ++e) {
+        const int m = F::out_index(tl, e);
+        pairspec[(size_t)q * M + m] = {(float)(r[e].x * scale), (float)(r[e].y * scale)};
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Forward FFT of windows of a row-major real matrix:  winspec[w] = FFT(src[row, t0 : t0+M])
+// with zeros outside [0, row_len).  win may be indexed indirectly through
+// `nwin_ptr` (device-side count) so the grid can be sized for the worst case.
+// ---------------------------------------------------------------------------
+template <int M>
+__device__ __forceinline__ void window_fft_body(const float* __restrict__ x, int row_len, int t0, int tl,
+                                                C32* sm, const C32* __restrict__ tw1, const C32* stw2,
+                                                C32* __restrict__ out) {
+    using F = BlockFft<M, float>;
+    C32 r[F::E];
+#pragma unroll
+    for (int e = 0; e < F::E; ++e) {
+        const int t = t0 + F::in_index(tl, e);
+        r[e] = {(t >= 0 && t < row_len) ? x[t] : 0.f, 0.f};
+    }
+    F::template pass1<-1>(r, tl, sm, tw1);
+    __syncthreads();
+    F::template pass2<-1>(r, tl, sm, stw2);
+    __syncthreads();
+    F::template pass3<-1>(r, tl, sm);
+#pragma unroll
+    for (int e = 0; e < F::E; ++e) out[F::out_index(tl, e)] = r[e];
+}
+
+template <int M>
+__global__ void __launch_bounds__(BlockFft<M, float>::T)
+k_window_fft(const float* __restrict__ src, long long row_stride, int row_len, const Win* __restrict__ win,
+             const C32* __restrict__ tw1, const C32* __restrict__ tw2, C32* __restrict__ winspec) {
+    using F = BlockFft<M, float>;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    C32* sm = reinterpret_cast<C32*>(smraw);
+    C32* stw2 = sm + F::SMEM_CPX;
+    const int tl = threadIdx.x, w = blockIdx.x;
+    for (int i = tl; i < 256; i += F::T) stw2[i] = tw2[i];
+    const Win wi = win[w];
+    __syncthreads();
+    window_fft_body<M>(src + (long long)wi.row * row_stride, row_len, wi.t0, tl, sm, tw1, stw2,
+                       winspec + (size_t)w * M);
+}
+
+// ---------------------------------------------------------------------------
+// THE HOT KERNEL.  For every (window w, atom pair q):
+//     y = IFFT_M( winspec[w] * pairspec[q] )          (fused complex multiply)
+//     Re y[m] = <window w shifted by m, atom 2q>,  Im y[m] = <..., atom 2q+1>,  m < nvb*blk
+// and then, depending on MODE,
+//     BLOCKMAX  max/argmax of every block of `blk` outputs -> bm_val/bm_pos
+//     ROWMAX    (only when each (row, pair) is visited by one CTA) re-reduce the
+//               two touched map rows over their NB block maxima -> row_val/row_pos
+//     DENSE     write the outputs to a dense destination (map, or Gram table)
+// grid = (ceil(pairs / NT), window groups); a CTA keeps its pair(s) and walks
+// the windows w = blockIdx.y, blockIdx.y + gridDim.y, ...
+// ---------------------------------------------------------------------------
+struct CorrArgs {
+    const C32* winspec;
+    const C32* pairspec;
+    const Win* win;
+    const int* nwin_ptr;  // optional device-side window count
+    int nwin;
+    int npairs;
+    int nloc;        // atoms owned by this plan (K_owned)
+    int len;         // row length N (valid outputs satisfy t0 + m < len)
+    int NB;          // block-max entries per row
+    int blk_shift;   // log2(blk)
+    const C32* tw1;
+    const C32* tw2;
+    float* bm_val;
+    int* bm_pos;
+    float* row_val;
+    int* row_pos;
+    float* dense;
+    long long dense_row_stride;   // between windows' source rows
+    long long dense_atom_stride;  // between atoms
+    int dense_col_off;            // column = t0 + m + dense_col_off
+};
+
+template <int M, int MODE>
+__global__ void __launch_bounds__((BlockFft<M, float>::T < 256 ? 256 : BlockFft<M, float>::T), 2)
+k_corr(const CorrArgs a) {
+    using F = BlockFft<M, float>;
+    constexpr int TPB = F::T < 256 ? 256 : F::T;
+    constexpr int NT = TPB / F::T;   // transforms (atom pairs) per CTA
+    constexpr int NW = F::T / 32;    // warps per transform
+    extern __shared__ __align__(16) unsigned char smraw[];
+    C32* stw2 = reinterpret_cast<C32*>(smraw);
+    const int sb = threadIdx.x / F::T, tl = threadIdx.x % F::T;
+    C32* sm = stw2 + 256 + (size_t)sb * F::SMEM_CPX;
+    for (int i = threadIdx.x; i < 256; i += TPB) stw2[i] = a.tw2[i];
+
+    int q = blockIdx.x * NT + sb;
+    const bool q_ok = q < a.npairs;
+    if (!q_ok) q = a.npairs - 1;
+    const C32* __restrict__ Eq = a.pairspec + (size_t)q * M;
+    const int nwin = a.nwin_ptr ? *a.nwin_ptr : a.nwin;
+    const int blk = 1 << a.blk_shift;
+    const int warp = tl >> 5, lane = tl & 31;
+    __syncthreads();
+
+    for (int w = blockIdx.y; w < nwin; w += gridDim.y) {
+        const Win wi = a.win[w];
+        const C32* __restrict__ X = a.winspec + (size_t)w * M;
+        C32 r[F::E];
+#pragma unroll
+        for (int e = 0; e < F::E; ++e) {
+            const int j = F::in_index(tl, e);
+            const float2 ev = __ldg(reinterpret_cast<const float2*>(Eq + j));
+            r[e] = cmul(ld_stream(X + j), C32{ev.x, ev.y});
+        }
+        F::template pass1<1>(r, tl, sm, a.tw1);
+        __syncthreads();
+        F::template pass2<1>(r, tl, sm, stw2);
+        __syncthreads();
+        F::template pass3<1>(r, tl, sm);
+
+        const int limit = min(wi.nvb * blk, a.len - wi.t0);   // valid outputs are m in [0, limit)
+        if constexpr ((MODE & MODE_DENSE) != 0) {
+            if (q_ok) {
+                float* base = a.dense + (long long)wi.row * a.dense_row_stride + (long long)(2 * q) * a.dense_atom_stride +
+                              (wi.t0 + a.dense_col_off);
+                const bool second = 2 * q + 1 < a.nloc;
+#pragma unroll
+                for (int e = 0; e < F::E; ++e) {
+                    const int m = F::out_index(tl, e);
+                    if (m < limit) {
+                        base[m] = r[e].x;
+                        if (second) base[a.dense_atom_stride + m] = r[e].y;
+                    }
+                }
+            }
+        }
+        if constexpr ((MODE & MODE_BLOCKMAX) != 0) {
+            __syncthreads();  // pass-3 loads finished: the buffer is reused as two real arrays
+            float* sA = reinterpret_cast<float*>(sm);
+            float* sB = sA + M;
+#pragma unroll
+            for (int e = 0; e < F::E; ++e) {
+                const int m = F::out_index(tl, e);
+                sA[m] = r[e].x + 0.f;  // +0: canonical zero, so ties behave like the reference's exact zeros
+                sB[m] = r[e].y + 0.f;
+            }
+            __syncthreads();
+            if (q_ok) {
+                for (int it = warp; it < 2 * wi.nvb; it += NW) {
+                    const int which = it & 1, i = it >> 1;
+                    const int k = 2 * q + which;
+                    if (k >= a.nloc) continue;
+                    const float* s = which ? sB : sA;
+                    const int hi = min((i + 1) * blk, limit);
+                    float v = -INFINITY;
+                    int at = INT_MAX;
+                    for (int m = i * blk + lane; m < hi; m += 32) {
+                        const float c = s[m];
+                        if (c > v) {
+                            v = c;
+                            at = m;
+                        }
+                    }
+                    warp_argmax(v, at);
+                    if (lane == 0) {
+                        const size_t o = ((size_t)wi.row * a.nloc + k) * a.NB + wi.blk0 + i;
+                        a.bm_val[o] = v;
+                        a.bm_pos[o] = (at == INT_MAX) ? INT_MAX : wi.t0 + at;
+                    }
+                }
+            }
+            if constexpr ((MODE & MODE_ROWMAX) != 0) {
+                __syncthreads();  // this CTA's block maxima are visible to all of its threads
+                if (q_ok) {
+                    for (int which = warp; which < 2; which += NW) {
+                        const int k = 2 * q + which;
+                        if (k >= a.nloc) continue;
+                        const size_t o = ((size_t)wi.row * a.nloc + k) * a.NB;
+                        float v = -INFINITY;
+                        int at = INT_MAX;
+                        for (int i = lane; i < a.NB; i += 32) {
+                            const float c = a.bm_val[o + i];
+                            if (c > v) {
+                                v = c;
+                                at = i;
+                            }
+                        }
+                        warp_argmax(v, at);
+                        if (lane == 0) {
+                            a.row_val[(size_t)wi.row * a.nloc + k] = v;
+                            a.row_pos[(size_t)wi.row * a.nloc + k] = (at == INT_MAX) ? 0 : a.bm_pos[o + at];
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();  // buffer free for the next window
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Row maxima over the block-max table (after a full pass). One warp per map row.
+// ---------------------------------------------------------------------------
+__global__ void k_rowmax(const float* __restrict__ bm_val, const int* __restrict__ bm_pos, int rows, int NB,
+                         float* __restrict__ row_val, int* __restrict__ row_pos) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const size_t o = (size_t)row * NB;
+    float v = -INFINITY;
+    int at = INT_MAX;
+    for (int i = lane; i < NB; i += 32) {
+        const float c = bm_val[o + i];
+        if (c > v) {
+            v = c;
+            at = i;
+        }
+    }
+    warp_argmax(v, at);
+    if (lane == 0) {
+        row_val[row] = v;
+        row_pos[row] = (at == INT_MAX) ? 0 : bm_pos[o + at];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Per-signal argmax over the owned rows -> Best record (global atom index).
+// One CTA of 256 threads per signal.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ Best block_best(const float* __restrict__ row_val, const int* __restrict__ row_pos,
+                                           int b, int nloc, int atom_lo, Best* s_best) {
+    float v = -INFINITY;
+    int k = INT_MAX;
+    for (int i = threadIdx.x; i < nloc; i += blockDim.x) {
+        const float c = row_val[(size_t)b * nloc + i];
+        if (c > v) {
+            v = c;
+            k = i;
+        }
+    }
+    warp_argmax(v, k);
+    __shared__ float s_v[32];
+    __shared__ int s_k[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        s_v[warp] = v;
+        s_k[warp] = k;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = blockDim.x >> 5;
+        v = lane < nw ? s_v[lane] : -INFINITY;
+        k = lane < nw ? s_k[lane] : INT_MAX;
+        warp_argmax(v, k);
+        if (lane == 0) {
+            Best best;
+            if (k == INT_MAX) {  // every candidate was NaN or -inf: fall back to the first entry
+                k = 0;
+                v = row_val[(size_t)b * nloc];
+            }
+            best.value = v;
+            best.atom = atom_lo + k;
+            best.position = row_pos[(size_t)b * nloc + k];
+            best.pad = 0;
+            *s_best = best;
+        }
+    }
+    __syncthreads();
+    return *s_best;
+}
+
+__global__ void __launch_bounds__(256)
+k_local_best(const float* __restrict__ row_val, const int* __restrict__ row_pos, int nloc, int atom_lo,
+             Best* __restrict__ best) {
+    __shared__ Best s_best;
+    const Best r = block_best(row_val, row_pos, blockIdx.x, nloc, atom_lo, &s_best);
+    if (threadIdx.x == 0) best[blockIdx.x] = r;
+}
+
+// Reduce candidates of several ranks: cand[r*batch + b] -> winner[b].
+// Larger value wins; equal values: lower atom, then lower position.
+__global__ void k_reduce_best(const Best* __restrict__ cand, int n_ranks, int batch, Best* __restrict__ winner) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    Best w = cand[b];
+    for (int r = 1; r < n_ranks; ++r) {
+        const Best c = cand[(size_t)r * batch + b];
+        if (c.value > w.value || (c.value == w.value && (c.atom < w.atom || (c.atom == w.atom && c.position < w.position))))
+            w = c;
+    }
+    winner[b] = w;
+}
+
+// ---------------------------------------------------------------------------
+// Apply one winner per signal: record it, subtract value*atom from the residual
+// (two roundings, like the reference: fl(r - fl(v*d)), modules/matchingpursuit.py:305, 328;
+// truncated at the right edge, :33-56), describe the +-A window whose block
+// maxima are now stale, and transform that window for the next correlation.
+// One CTA of 256 threads per signal.  SELECT: take the winner from this plan's
+// own rows instead of `winner`.
+// ---------------------------------------------------------------------------
+struct ApplyArgs {
+    const float* row_val;
+    const int* row_pos;
+    const Best* winner;   // used when !SELECT
+    const float* dict;    // whole unit dictionary (K, A)
+    float* residual;      // (B, N)
+    int nloc, atom_lo, A, N, blk_shift, NB;
+    int step, n_steps;
+    int* atom_out;        // (B, n_steps) or null
+    int* pos_out;
+    float* val_out;
+    Win* win;             // (B)
+    const C32* tw1;
+    const C32* tw2;
+    C32* winspec;         // (B, M)
+    int do_fft;           // 0 on the last step
+};
+
+template <int M, bool SELECT>
+__global__ void __launch_bounds__(256)
+k_apply(const ApplyArgs a) {
+    using F = BlockFft<M, float>;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    C32* sm = reinterpret_cast<C32*>(smraw);
+    C32* stw2 = sm + F::SMEM_CPX;
+    __shared__ Best s_best;
+    const int b = blockIdx.x;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) stw2[i] = a.tw2[i];
+    Best w;
+    if constexpr (SELECT) {
+        w = block_best(a.row_val, a.row_pos, b, a.nloc, a.atom_lo, &s_best);
+    } else {
+        w = a.winner[b];
+    }
+    const int p = w.position;
+    if (threadIdx.x == 0 && a.atom_out) {
+        a.atom_out[(size_t)b * a.n_steps + a.step] = w.atom;
+        a.pos_out[(size_t)b * a.n_steps + a.step] = p;
+        a.val_out[(size_t)b * a.n_steps + a.step] = w.value;
+    }
+    float* __restrict__ r = a.residual + (size_t)b * a.N;
+    const float* __restrict__ d = a.dict + (size_t)w.atom * a.A;
+    const int keep = min(a.A, a.N - p);
+    for (int i = threadIdx.x; i < keep; i += blockDim.x) r[p + i] = __fsub_rn(r[p + i], __fmul_rn(w.value, d[i]));
+    const int first = max(0, p - a.A + 1), last = min(a.N - 1, p + a.A - 1);
+    Win wi;
+    wi.row = b;
+    wi.blk0 = first >> a.blk_shift;
+    wi.t0 = wi.blk0 << a.blk_shift;
+    wi.nvb = (last >> a.blk_shift) - wi.blk0 + 1;
+    if (threadIdx.x == 0) a.win[b] = wi;
+    __syncthreads();  // residual writes of this CTA are visible to its own loads below
+    if (a.do_fft) {
+        const int tl = threadIdx.x;
+        C32 rr[F::E];
+        if (tl < F::T) {
+#pragma unroll
+            for (int e = 0; e < F::E; ++e) {
+                const int t = wi.t0 + F::in_index(tl, e);
+                rr[e] = {(t < a.N) ? r[t] : 0.f, 0.f};
+            }
+            F::template pass1<-1>(rr, tl, sm, a.tw1);
+        }
+        __syncthreads();
+        if (tl < F::T) F::template pass2<-1>(rr, tl, sm, stw2);
+        __syncthreads();
+        if (tl < F::T) {
+            F::template pass3<-1>(rr, tl, sm);
+            C32* out = a.winspec + (size_t)b * M;
+#pragma unroll
+            for (int e = 0; e < F::E; ++e) out[F::out_index(tl, e)] = rr[e];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Decode helpers (modules/matchingpursuit.py:20-58, :305).
+// ---------------------------------------------------------------------------
+// Deterministic: a thread owns output samples and walks the events in list
+// order, so overlapping atoms are summed in the reference's order.
+// grid = (ceil(N / 1024), batch), 256 threads, 4 samples per thread.
+__global__ void __launch_bounds__(256)
+k_scatter_add(float* __restrict__ out, int batch, int N, const float* __restrict__ dict, int K, int A,
+              const int* __restrict__ atom, const int* __restrict__ bidx, const int* __restrict__ pos,
+              const float* __restrict__ val, int n_events) {
+    const int b = blockIdx.y;
+    const int tile0 = blockIdx.x * 1024;
+    float acc[4];
+    int t[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        t[u] = tile0 + threadIdx.x + 256 * u;
+        acc[u] = t[u] < N ? out[(size_t)b * N + t[u]] : 0.f;
+    }
+    for (int e = 0; e < n_events; ++e) {
+        if (bidx[e] != b) continue;
+        const int p = pos[e], k = atom[e];
+        if (k < 0 || k >= K || p + A <= tile0 || p >= tile0 + 1024 || p < 0) continue;
+        const float v = val[e];
+        const float* d = dict + (size_t)k * A;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = t[u] - p;
+            if (i >= 0 && i < A) acc[u] = __fadd_rn(acc[u], __fmul_rn(v, d[i]));
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        if (t[u] < N) out[(size_t)b * N + t[u]] = acc[u];
+}
+
+__global__ void k_gather_atoms(float* __restrict__ scaled, const float* __restrict__ dict, int K, int A,
+                               const int* __restrict__ atom, const float* __restrict__ val, int n_events) {
+    const int e = blockIdx.x;
+    if (e >= n_events) return;
+    const int k = atom[e];
+    const float v = val[e];
+    const float* d = dict + (size_t)k * A;
+    float* o = scaled + (size_t)e * A;
+    for (int i = threadIdx.x; i < A; i += blockDim.x) o[i] = (k >= 0 && k < K) ? __fmul_rn(d[i], v) : 0.f;
+}
+
+}  // namespace mpb

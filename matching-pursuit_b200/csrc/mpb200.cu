@@ -1,0 +1,595 @@
+// mpb200.cu -- plan management and the extern "C" entry points of include/mpb200.h.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
+//             -Xcompiler -fPIC -shared -o libmpb200.so mpb200.cu fftconv.cu
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mpb200.h"
+#include "kernels.cuh"
+#include "plan.h"
+
+namespace mpb {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define MPB_CUDA(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return fail(MPB200_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+    } while (0)
+
+#define MPB_LAUNCH_CHECK(name)                                                                  \
+    do {                                                                                        \
+        cudaError_t _e = cudaGetLastError();                                                    \
+        if (_e != cudaSuccess)                                                                  \
+            return fail(MPB200_ECUDA, std::string("launch ") + name + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+#define MPB_DISPATCH_M(m, ...)                                            \
+    switch (m) {                                                          \
+        case 512: { constexpr int MM = 512; __VA_ARGS__; } break;         \
+        case 1024: { constexpr int MM = 1024; __VA_ARGS__; } break;       \
+        case 2048: { constexpr int MM = 2048; __VA_ARGS__; } break;       \
+        case 4096: { constexpr int MM = 4096; __VA_ARGS__; } break;       \
+        case 8192: { constexpr int MM = 8192; __VA_ARGS__; } break;       \
+        default: return fail(MPB200_EINVAL, "unsupported FFT size");      \
+    }
+
+template <typename K>
+static cudaError_t allow_smem(K kernel, size_t bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+// ---------------------------------------------------------------------------
+// geometry
+// ---------------------------------------------------------------------------
+int choose_fft_size(int A) {
+    // a step window refreshes up to span = ceil((2A-2)/blk)+1 blocks of blk = M/32 outputs and
+    // needs span*blk + A - 1 <= 3A - 3 + M/16 input samples  ->  M >= (3A-3)*16/15
+    const long long need = ((long long)(3 * A - 3) * 16 + 14) / 15;
+    for (int m = 512; m <= 8192; m *= 2)
+        if (m >= need && m >= A + m / 32) return m;
+    return 0;
+}
+
+template <typename Real>
+static void host_twiddles(int M, std::vector<cpx<Real>>& t1, std::vector<cpx<Real>>& t2) {
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    const int R1 = M / 256;
+    t1.resize(M);
+    t2.resize(256);
+    for (int m1 = 0; m1 < R1; ++m1)
+        for (int c = 0; c < 256; ++c) {
+            long double a = two_pi * (long double)(((long long)c * m1) % M) / (long double)M;
+            t1[m1 * 256 + c] = {(Real)cosl(a), (Real)sinl(a)};
+        }
+    for (int m2 = 0; m2 < 16; ++m2)
+        for (int j3 = 0; j3 < 16; ++j3) {
+            long double a = two_pi * (long double)((j3 * m2) % 256) / 256.0L;
+            t2[m2 * 16 + j3] = {(Real)cosl(a), (Real)sinl(a)};
+        }
+}
+
+template <typename T>
+static int dev_alloc(Plan* p, T** ptr, size_t count) {
+    *ptr = nullptr;
+    if (count == 0) return MPB200_OK;
+    cudaError_t e = cudaMalloc((void**)ptr, count * sizeof(T));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(MPB200_ENOMEM, "cudaMalloc of " + std::to_string(count * sizeof(T)) + " bytes failed: " +
+                                       cudaGetErrorString(e));
+    }
+    p->allocs.push_back((void*)*ptr);
+    p->bytes += count * sizeof(T);
+    return MPB200_OK;
+}
+
+static void free_plan(Plan* p) {
+    for (void* q : p->allocs) cudaFree(q);
+    if (p->h_stage) cudaFreeHost(p->h_stage);
+    delete p;
+}
+
+// ---------------------------------------------------------------------------
+// launches
+// ---------------------------------------------------------------------------
+static int launch_window_fft(Plan* p, const float* src, long long row_stride, int row_len, const Win* win, int nwin,
+                             C32* winspec, cudaStream_t st) {
+    if (nwin <= 0) return MPB200_OK;
+    MPB_DISPATCH_M(p->M, {
+        using F = BlockFft<MM, float>;
+        const size_t smem = (size_t)(F::SMEM_CPX + 256) * sizeof(C32);
+        static bool once = false;
+        if (!once) { MPB_CUDA(allow_smem(k_window_fft<MM>, smem)); once = true; }
+        k_window_fft<MM><<<nwin, F::T, smem, st>>>(src, row_stride, row_len, win, p->tw1, p->tw2, winspec);
+    });
+    MPB_LAUNCH_CHECK("k_window_fft");
+    return MPB200_OK;
+}
+
+template <int MODE>
+static int launch_corr(Plan* p, CorrArgs a, int groups, cudaStream_t st) {
+    if (a.nwin <= 0) return MPB200_OK;
+    MPB_DISPATCH_M(p->M, {
+        using F = BlockFft<MM, float>;
+        constexpr int TPB = F::T < 256 ? 256 : F::T;
+        constexpr int NT = TPB / F::T;
+        const size_t smem = (size_t)(256 + NT * F::SMEM_CPX) * sizeof(C32);
+        static bool once = false;
+        if (!once) { MPB_CUDA(allow_smem(k_corr<MM, MODE>, smem)); once = true; }
+        dim3 grid((a.npairs + NT - 1) / NT, groups);
+        k_corr<MM, MODE><<<grid, TPB, smem, st>>>(a);
+    });
+    MPB_LAUNCH_CHECK("k_corr");
+    return MPB200_OK;
+}
+
+static int corr_groups(const Plan* p, int nwin) {
+    const int tpb_pairs = (p->M >= 4096) ? 1 : (4096 / p->M > 8 ? 8 : 4096 / p->M);  // NT of k_corr
+    const int gx = (p->npairs + tpb_pairs - 1) / tpb_pairs;
+    int g = (p->sm_count * 8 + gx - 1) / gx;
+    if (g < 1) g = 1;
+    if (g > nwin) g = nwin;
+    if (g > 65535) g = 65535;
+    return g;
+}
+
+static CorrArgs base_corr_args(const Plan* p) {
+    CorrArgs a;
+    memset(&a, 0, sizeof(a));
+    a.winspec = p->winspec;
+    a.pairspec = p->pairspec;
+    a.npairs = p->npairs;
+    a.nloc = p->nloc;
+    a.len = p->N;
+    a.NB = p->NB;
+    a.blk_shift = p->blk_shift;
+    a.tw1 = p->tw1;
+    a.tw2 = p->tw2;
+    a.bm_val = p->bm_val;
+    a.bm_pos = p->bm_pos;
+    a.row_val = p->row_val;
+    a.row_pos = p->row_pos;
+    return a;
+}
+
+// Full correlation of the current residual: block maxima (and the dense map
+// when `dense` is given) for all positions, in slabs of at most wcap windows.
+static int full_pass(Plan* p, int batch, float* dense, cudaStream_t st) {
+    const int total = batch * p->nchunks;
+    for (int w0 = 0; w0 < total; w0 += p->wcap) {
+        const int n = total - w0 < p->wcap ? total - w0 : p->wcap;
+        int rc = launch_window_fft(p, p->residual, p->N, p->N, p->win_full + w0, n, p->winspec, st);
+        if (rc) return rc;
+        CorrArgs a = base_corr_args(p);
+        a.win = p->win_full + w0;
+        a.nwin = n;
+        if (dense) {
+            a.dense = dense;
+            a.dense_row_stride = (long long)p->nloc * p->N;
+            a.dense_atom_stride = p->N;
+            a.dense_col_off = 0;
+            rc = launch_corr<MODE_DENSE>(p, a, corr_groups(p, n), st);
+        } else {
+            rc = launch_corr<MODE_BLOCKMAX>(p, a, corr_groups(p, n), st);
+        }
+        if (rc) return rc;
+    }
+    if (!dense) {
+        const int rows = batch * p->nloc;
+        k_rowmax<<<(rows + 7) / 8, 256, 0, st>>>(p->bm_val, p->bm_pos, rows, p->NB, p->row_val, p->row_pos);
+        MPB_LAUNCH_CHECK("k_rowmax");
+    }
+    return MPB200_OK;
+}
+
+template <bool SELECT>
+static int launch_apply(Plan* p, int batch, const Best* winner, int step, int n_steps, int* atom_out, int* pos_out,
+                        float* val_out, int do_fft, cudaStream_t st) {
+    ApplyArgs a;
+    memset(&a, 0, sizeof(a));
+    a.row_val = p->row_val;
+    a.row_pos = p->row_pos;
+    a.winner = winner;
+    a.dict = p->dict;
+    a.residual = p->residual;
+    a.nloc = p->nloc;
+    a.atom_lo = p->lo;
+    a.A = p->A;
+    a.N = p->N;
+    a.blk_shift = p->blk_shift;
+    a.NB = p->NB;
+    a.step = step;
+    a.n_steps = n_steps;
+    a.atom_out = atom_out;
+    a.pos_out = pos_out;
+    a.val_out = val_out;
+    a.win = p->win_step;
+    a.tw1 = p->tw1;
+    a.tw2 = p->tw2;
+    a.winspec = p->winspec;
+    a.do_fft = do_fft;
+    MPB_DISPATCH_M(p->M, {
+        using F = BlockFft<MM, float>;
+        const size_t smem = (size_t)(F::SMEM_CPX + 256) * sizeof(C32);
+        static bool once = false;
+        if (!once) { MPB_CUDA((allow_smem(k_apply<MM, SELECT>, smem))); once = true; }
+        k_apply<MM, SELECT><<<batch, 256, smem, st>>>(a);
+    });
+    MPB_LAUNCH_CHECK("k_apply");
+    return MPB200_OK;
+}
+
+// Refresh the block maxima (and row maxima) of the windows written by k_apply.
+static int step_refresh(Plan* p, int batch, cudaStream_t st) {
+    if (p->mode == MPB200_MODE_FULL) return full_pass(p, batch, nullptr, st);
+    CorrArgs a = base_corr_args(p);
+    a.win = p->win_step;
+    a.nwin = batch;
+    return launch_corr<MODE_BLOCKMAX | MODE_ROWMAX>(p, a, corr_groups(p, batch), st);
+}
+
+static int build_pair_spectra(Plan* p, cudaStream_t st) {
+    MPB_DISPATCH_M(p->M, {
+        using F = BlockFft<MM, double>;
+        const size_t smem = (size_t)(F::SMEM_CPX + 256) * sizeof(cpx<double>);
+        static bool once = false;
+        if (!once) { MPB_CUDA((allow_smem(k_pair_spectra<MM, double>, smem))); once = true; }
+        k_pair_spectra<MM, double><<<p->npairs, F::T, smem, st>>>(p->dict, p->A, p->lo, p->hi, p->tw1d, p->tw2d,
+                                                                   p->pairspec);
+    });
+    MPB_LAUNCH_CHECK("k_pair_spectra");
+    return MPB200_OK;
+}
+
+static int check_plan(Plan* p, bool need_dict) {
+    if (!p) return fail(MPB200_EINVAL, "null plan");
+    if (need_dict && !p->dict_set) return fail(MPB200_ESTATE, "mpb200_plan_set_dictionary has not been called");
+    cudaError_t e = cudaSetDevice(p->device);
+    if (e != cudaSuccess) return fail(MPB200_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    return MPB200_OK;
+}
+
+}  // namespace mpb
+
+using namespace mpb;
+
+extern "C" {
+
+int mpb200_version(void) { return MPB200_VERSION; }
+
+const char* mpb200_last_error(void) { return g_last_error.c_str(); }
+
+int mpb200_plan_create(mpb200_plan_t* out, int n_atoms, int atom_size, int n_samples, int max_batch, int mode,
+                       int atom_lo, int atom_hi, uint64_t gram_budget_bytes) {
+    if (!out) return fail(MPB200_EINVAL, "null plan pointer");
+    *out = nullptr;
+    if (n_atoms < 1 || atom_size < 1 || n_samples < 1 || max_batch < 1)
+        return fail(MPB200_EINVAL, "n_atoms, atom_size, n_samples and max_batch must be positive");
+    if (atom_lo == 0 && atom_hi == 0) atom_hi = n_atoms;
+    if (atom_lo < 0 || atom_hi > n_atoms || atom_lo >= atom_hi)
+        return fail(MPB200_EINVAL, "atom shard [atom_lo, atom_hi) must be a non-empty sub-range of [0, n_atoms)");
+    if (mode < MPB200_MODE_AUTO || mode > MPB200_MODE_FULL) return fail(MPB200_EINVAL, "unknown mode");
+    const int M = choose_fft_size(atom_size);
+    if (M == 0)
+        return fail(MPB200_EINVAL, "atom_size " + std::to_string(atom_size) +
+                                       " needs a window FFT longer than 8192 (supported: atom_size <= 2560)");
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || count == 0)
+        return fail(MPB200_ECUDA, "no CUDA device: this library has no CPU path");
+    Plan* p = new Plan();
+    MPB_CUDA(cudaGetDevice(&p->device));
+    cudaDeviceProp prop;
+    MPB_CUDA(cudaGetDeviceProperties(&prop, p->device));
+    p->sm_count = prop.multiProcessorCount;
+    p->K = n_atoms;
+    p->A = atom_size;
+    p->N = n_samples;
+    p->Bmax = max_batch;
+    p->lo = atom_lo;
+    p->hi = atom_hi;
+    p->nloc = atom_hi - atom_lo;
+    p->npairs = (p->nloc + 1) / 2;
+    p->M = M;
+    p->blk = M / 32;
+    p->blk_shift = 0;
+    while ((1 << p->blk_shift) < p->blk) ++p->blk_shift;
+    p->NB = (n_samples + p->blk - 1) / p->blk;
+    p->vfull = (M - atom_size + 1) / p->blk;
+    if (p->vfull > 32) p->vfull = 32;
+    p->nchunks = (p->NB + p->vfull - 1) / p->vfull;
+
+    // Gram table: (nloc, K?) -- the table is indexed [winner atom (any of K)][owned atom][lag]
+    const uint64_t gram_bytes = (uint64_t)n_atoms * p->nloc * (2ull * atom_size) * sizeof(float);
+    const uint64_t map_bytes = (uint64_t)max_batch * p->nloc * n_samples * sizeof(float);
+    if (mode == MPB200_MODE_AUTO) {
+        size_t free_b = 0, total_b = 0;
+        MPB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        uint64_t budget = gram_budget_bytes ? gram_budget_bytes : (uint64_t)(0.4 * (double)free_b);
+        mode = (gram_bytes <= budget && gram_bytes + map_bytes <= (uint64_t)(0.8 * (double)free_b))
+                   ? MPB200_MODE_GRAM : MPB200_MODE_RECORRELATE;
+    }
+    p->mode = mode;
+    if (mode == MPB200_MODE_GRAM) {
+        free_plan(p);
+        return fail(MPB200_EINVAL, "GRAM mode is not built into this library version");
+    }
+
+    int rc = MPB200_OK;
+    std::vector<cpx<float>> t1, t2;
+    std::vector<cpx<double>> t1d, t2d;
+    host_twiddles<float>(M, t1, t2);
+    host_twiddles<double>(M, t1d, t2d);
+    const long long total_full = (long long)max_batch * p->nchunks;
+    p->wcap = (int)(total_full < 2048 ? total_full : 2048);
+    if (p->wcap < max_batch) p->wcap = max_batch;
+    std::vector<Win> wf((size_t)total_full);
+    for (int b = 0; b < max_batch; ++b)
+        for (int c = 0; c < p->nchunks; ++c) {
+            Win w;
+            w.row = b;
+            w.blk0 = c * p->vfull;
+            w.t0 = w.blk0 * p->blk;
+            w.nvb = (p->NB - w.blk0 < p->vfull) ? p->NB - w.blk0 : p->vfull;
+            wf[(size_t)b * p->nchunks + c] = w;
+        }
+#define MPB_TRY(x) do { rc = (x); if (rc) { free_plan(p); return rc; } } while (0)
+    MPB_TRY(dev_alloc(p, &p->dict, (size_t)n_atoms * atom_size));
+    MPB_TRY(dev_alloc(p, &p->pairspec, (size_t)p->npairs * M));
+    MPB_TRY(dev_alloc(p, &p->tw1, (size_t)M));
+    MPB_TRY(dev_alloc(p, &p->tw2, (size_t)256));
+    MPB_TRY(dev_alloc(p, &p->tw1d, (size_t)M));
+    MPB_TRY(dev_alloc(p, &p->tw2d, (size_t)256));
+    MPB_TRY(dev_alloc(p, &p->winspec, (size_t)p->wcap * M));
+    MPB_TRY(dev_alloc(p, &p->win_full, (size_t)total_full));
+    MPB_TRY(dev_alloc(p, &p->win_step, (size_t)max_batch));
+    MPB_TRY(dev_alloc(p, &p->bm_val, (size_t)max_batch * p->nloc * p->NB));
+    MPB_TRY(dev_alloc(p, &p->bm_pos, (size_t)max_batch * p->nloc * p->NB));
+    MPB_TRY(dev_alloc(p, &p->row_val, (size_t)max_batch * p->nloc));
+    MPB_TRY(dev_alloc(p, &p->row_pos, (size_t)max_batch * p->nloc));
+    MPB_TRY(dev_alloc(p, &p->residual, (size_t)max_batch * n_samples));
+    MPB_TRY(dev_alloc(p, &p->best, (size_t)max_batch));
+#undef MPB_TRY
+    cudaError_t e = cudaSuccess;
+    auto up = [&](void* dst, const void* src, size_t bytes) {
+        if (e == cudaSuccess) e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    };
+    up(p->tw1, t1.data(), t1.size() * sizeof(t1[0]));
+    up(p->tw2, t2.data(), t2.size() * sizeof(t2[0]));
+    up(p->tw1d, t1d.data(), t1d.size() * sizeof(t1d[0]));
+    up(p->tw2d, t2d.data(), t2d.size() * sizeof(t2d[0]));
+    up(p->win_full, wf.data(), wf.size() * sizeof(Win));
+    if (e != cudaSuccess) {
+        free_plan(p);
+        return fail(MPB200_ECUDA, std::string("table upload: ") + cudaGetErrorString(e));
+    }
+    *out = reinterpret_cast<mpb200_plan_t>(p);
+    return MPB200_OK;
+}
+
+int mpb200_plan_destroy(mpb200_plan_t plan) {
+    Plan* p = reinterpret_cast<Plan*>(plan);
+    if (!p) return MPB200_OK;
+    cudaSetDevice(p->device);
+    cudaDeviceSynchronize();
+    free_plan(p);
+    return MPB200_OK;
+}
+
+int mpb200_plan_info_get(mpb200_plan_t plan, mpb200_plan_info* info) {
+    Plan* p = reinterpret_cast<Plan*>(plan);
+    if (!p || !info) return fail(MPB200_EINVAL, "null argument");
+    memset(info, 0, sizeof(*info));
+    info->n_atoms = p->K;
+    info->atom_size = p->A;
+    info->n_samples = p->N;
+    info->max_batch = p->Bmax;
+    info->mode = p->mode;
+    info->fft_size = p->M;
+    info->block = p->blk;
+    info->n_blocks = p->NB;
+    info->atom_lo = p->lo;
+    info->atom_hi = p->hi;
+    info->device_bytes = p->bytes;
+    info->gram_bytes = p->gram_bytes;
+    return MPB200_OK;
+}
+
+int mpb200_plan_set_dictionary(mpb200_plan_t plan, const float* d, void* stream) {
+    Plan* p = reinterpret_cast<Plan*>(plan);
+    int rc = check_plan(p, false);
+    if (rc) return rc;
+    if (!d) return fail(MPB200_EINVAL, "null dictionary");
+    cudaStream_t st = (cudaStream_t)stream;
+    k_unit_norm<<<(p->K + 7) / 8, 256, 0, st>>>(d, p->dict, p->K, p->A, 1e-8f);
+    MPB_LAUNCH_CHECK("k_unit_norm");
+    rc = build_pair_spectra(p, st);
+    if (rc) return rc;
+    p->dict_set = true;
+    p->cur_batch = 0;
+    return MPB200_OK;
+}
+
+int mpb200_plan_get_unit_dictionary(mpb200_plan_t plan, float* out, void* stream) {
+    Plan* p = reinterpret_cast<Plan*>(plan);
+    int rc = check_plan(p, true);
+    if (rc) return rc;
+    MPB_CUDA(cudaMemcpyAsync(out, p->dict, (size_t)p->K * p->A * sizeof(float), cudaMemcpyDeviceToDevice,
+                             (cudaStream_t)stream));
+    return MPB200_OK;
+}
+
+int mpb200_begin(mpb200_plan_t plan, const float* signal, int batch, void* stream) {
+    Plan* p = reinterpret_cast<Plan*>(plan);
+    int rc = check_plan(p, true);
+    if (rc) return rc;
+    if (batch < 1 || batch > p->Bmax) return fail(MPB200_EINVAL, "batch must be in [1, max_batch]");
+    if (!signal) return fail(MPB200_EINVAL, "null signal");
+    cudaStream_t st = (cudaStream_t)stream;
+    MPB_CUDA(cudaMemcpyAsync(p->residual, signal, (size_t)batch * p->N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    p->cur_batch = batch;
+    return full_pass(p, batch, nullptr, st);
+}
+
+int mpb200_local_best(mpb200_plan_t plan, mpb200_best* best, void* stream) {
+    Plan* p = reinterpret_cast<Plan*>(plan);
+    int rc = check_plan(p, true);
+    if (rc) return rc;
+    if (p->cur_batch < 1) return fail(MPB200_ESTATE, "mpb200_begin has not been called");
+    k_local_best<<<p->cur_batch, 256, 0, (cudaStream_t)stream>>>(p->row_val, p->row_pos, p->nloc, p->lo,
+                                                                  reinterpret_cast<Best*>(best));
+    MPB_LAUNCH_CHECK("k_local_best");
+    return MPB200_OK;
+}
+
+int mpb200_apply(mpb200_plan_t plan, const mpb200_best* winner, void* stream) {
+    Plan* p = reinterpret_cast<Plan*>(plan);
+    int rc = check_plan(p, true);
+    if (rc) return rc;
+    if (p->cur_batch < 1) return fail(MPB200_ESTATE, "mpb200_begin has not been called");
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = launch_apply<false>(p, p->cur_batch, reinterpret_cast<const Best*>(winner), 0, 1, nullptr, nullptr, nullptr,
+                             p->mode != MPB200_MODE_FULL, st);
+    if (rc) return rc;
+    return step_refresh(p, p->cur_batch, st);
+}
+
+int mpb200_residual(mpb200_plan_t plan, float* residual_out, void* stream) {
+    Plan* p = reinterpret_cast<Plan*>(plan);
+    int rc = check_plan(p, true);
+    if (rc) return rc;
+    if (p->cur_batch < 1) return fail(MPB200_ESTATE, "mpb200_begin has not been called");
+    MPB_CUDA(cudaMemcpyAsync(residual_out, p->residual, (size_t)p->cur_batch * p->N * sizeof(float),
+                             cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return MPB200_OK;
+}
+
+int mpb200_reduce_best(const mpb200_best* cand, int n_ranks, int batch, mpb200_best* winner, void* stream) {
+    if (!cand || !winner || n_ranks < 1 || batch < 1) return fail(MPB200_EINVAL, "bad argument");
+    k_reduce_best<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const Best*>(cand), n_ranks,
+                                                                         batch, reinterpret_cast<Best*>(winner));
+    MPB_LAUNCH_CHECK("k_reduce_best");
+    return MPB200_OK;
+}
+
+int mpb200_sparse_code(mpb200_plan_t plan, const float* signal, int batch, int n_steps, float* residual_out,
+                       int32_t* atom_out, int32_t* pos_out, float* val_out, void* stream) {
+    Plan* p = reinterpret_cast<Plan*>(plan);
+    if (n_steps < 0) return fail(MPB200_EINVAL, "n_steps must be >= 0");
+    if (n_steps > 0 && (!atom_out || !pos_out || !val_out)) return fail(MPB200_EINVAL, "null output");
+    if (p && (p->lo != 0 || p->hi != p->K))
+        return fail(MPB200_ESTATE, "mpb200_sparse_code needs a plan that owns every atom; "
+                                   "sharded plans use begin/local_best/apply");
+    int rc = mpb200_begin(plan, signal, batch, stream);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int s = 0; s < n_steps; ++s) {
+        const bool last = (s == n_steps - 1);
+        rc = launch_apply<true>(p, batch, nullptr, s, n_steps, atom_out, pos_out, val_out,
+                                (!last && p->mode != MPB200_MODE_FULL) ? 1 : 0, st);
+        if (rc) return rc;
+        if (!last) {
+            rc = step_refresh(p, batch, st);
+            if (rc) return rc;
+        }
+    }
+    if (n_steps > 0) p->cur_batch = 0;  // block maxima are stale after the last subtraction
+    if (residual_out)
+        MPB_CUDA(cudaMemcpyAsync(residual_out, p->residual, (size_t)batch * p->N * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, st));
+    return MPB200_OK;
+}
+
+int mpb200_sparse_code_host(mpb200_plan_t plan, const float* signal_host, int batch, int n_steps,
+                            float* residual_out_host, int32_t* atom_out_host, int32_t* pos_out_host,
+                            float* val_out_host, void* stream) {
+    Plan* p = reinterpret_cast<Plan*>(plan);
+    int rc = check_plan(p, true);
+    if (rc) return rc;
+    if (batch < 1 || batch > p->Bmax) return fail(MPB200_EINVAL, "batch must be in [1, max_batch]");
+    if (n_steps < 0 || !signal_host) return fail(MPB200_EINVAL, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t sig_bytes = (size_t)batch * p->N * sizeof(float);
+    const size_t ev = (size_t)batch * (size_t)n_steps;
+    if (!p->d_signal) {
+        rc = dev_alloc(p, &p->d_signal, (size_t)p->Bmax * p->N);
+        if (rc) return rc;
+    }
+    if (ev > p->ev_cap) {
+        // event staging grows with n_steps; old buffers stay owned by the plan until destroy
+        rc = dev_alloc(p, &p->d_atom, ev);
+        if (!rc) rc = dev_alloc(p, &p->d_pos, ev);
+        if (!rc) rc = dev_alloc(p, &p->d_val, ev);
+        if (rc) return rc;
+        p->ev_cap = ev;
+    }
+    MPB_CUDA(cudaMemcpyAsync(p->d_signal, signal_host, sig_bytes, cudaMemcpyHostToDevice, st));
+    rc = mpb200_sparse_code(plan, p->d_signal, batch, n_steps, nullptr, p->d_atom, p->d_pos, p->d_val, stream);
+    if (rc) return rc;
+    if (n_steps > 0) {
+        MPB_CUDA(cudaMemcpyAsync(atom_out_host, p->d_atom, ev * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        MPB_CUDA(cudaMemcpyAsync(pos_out_host, p->d_pos, ev * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        MPB_CUDA(cudaMemcpyAsync(val_out_host, p->d_val, ev * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    if (residual_out_host)
+        MPB_CUDA(cudaMemcpyAsync(residual_out_host, p->residual, sig_bytes, cudaMemcpyDeviceToHost, st));
+    MPB_CUDA(cudaStreamSynchronize(st));
+    return MPB200_OK;
+}
+
+int mpb200_correlate(mpb200_plan_t plan, const float* signal, int batch, float* fm_out, void* stream) {
+    Plan* p = reinterpret_cast<Plan*>(plan);
+    int rc = check_plan(p, true);
+    if (rc) return rc;
+    if (batch < 1 || batch > p->Bmax) return fail(MPB200_EINVAL, "batch must be in [1, max_batch]");
+    if (!signal || !fm_out) return fail(MPB200_EINVAL, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    MPB_CUDA(cudaMemcpyAsync(p->residual, signal, (size_t)batch * p->N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    p->cur_batch = 0;
+    return full_pass(p, batch, fm_out, st);
+}
+
+int mpb200_scatter_add(float* out, int batch, int n_samples, const float* d_unit, int n_atoms, int atom_size,
+                       const int32_t* atom, const int32_t* batch_index, const int32_t* pos, const float* val,
+                       int n_events, void* stream) {
+    if (!out || !d_unit || batch < 1 || n_samples < 1 || n_atoms < 1 || atom_size < 1 || n_events < 0)
+        return fail(MPB200_EINVAL, "bad argument");
+    if (n_events == 0) return MPB200_OK;
+    if (!atom || !batch_index || !pos || !val) return fail(MPB200_EINVAL, "null event array");
+    dim3 grid((n_samples + 1023) / 1024, batch);
+    k_scatter_add<<<grid, 256, 0, (cudaStream_t)stream>>>(out, batch, n_samples, d_unit, n_atoms, atom_size, atom,
+                                                          batch_index, pos, val, n_events);
+    MPB_LAUNCH_CHECK("k_scatter_add");
+    return MPB200_OK;
+}
+
+int mpb200_gather_atoms(float* scaled, const float* d_unit, int n_atoms, int atom_size, const int32_t* atom,
+                        const float* val, int n_events, void* stream) {
+    if (!scaled || !d_unit || !atom || !val || n_atoms < 1 || atom_size < 1 || n_events < 0)
+        return fail(MPB200_EINVAL, "bad argument");
+    if (n_events == 0) return MPB200_OK;
+    k_gather_atoms<<<n_events, 128, 0, (cudaStream_t)stream>>>(scaled, d_unit, n_atoms, atom_size, atom, val, n_events);
+    MPB_LAUNCH_CHECK("k_gather_atoms");
+    return MPB200_OK;
+}
+
+int mpb200_unit_norm(const float* x, float* y, int rows, int cols, float eps, void* stream) {
+    if (!x || !y || rows < 1 || cols < 1) return fail(MPB200_EINVAL, "bad argument");
+    k_unit_norm<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, y, rows, cols, eps);
+    MPB_LAUNCH_CHECK("k_unit_norm");
+    return MPB200_OK;
+}
+
+}  // extern "C"

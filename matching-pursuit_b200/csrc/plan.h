@@ -1,0 +1,54 @@
+// plan.h -- host-side state behind an mpb200_plan_t.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "types.h"
+
+namespace mpb {
+
+struct Plan {
+    int device = 0, sm_count = 148;
+    int K = 0, A = 0, N = 0, Bmax = 0, mode = 0;
+    int lo = 0, hi = 0, nloc = 0, npairs = 0;       // owned atom range
+    int M = 0, blk = 0, blk_shift = 0, NB = 0;      // window FFT size, block-max granularity
+    int vfull = 0, nchunks = 0;                     // full pass: blocks per window, windows per signal
+    int wcap = 0;                                   // window-spectrum slots
+    int cur_batch = 0;                              // batch loaded by mpb200_begin (0 = none)
+    bool dict_set = false;
+
+    float* dict = nullptr;          // (K, A) unit-normed
+    C32* pairspec = nullptr;        // (npairs, M)
+    C32 *tw1 = nullptr, *tw2 = nullptr;
+    cpx<double> *tw1d = nullptr, *tw2d = nullptr;
+    C32* winspec = nullptr;         // (wcap, M)
+    Win* win_full = nullptr;        // (Bmax * nchunks)
+    Win* win_step = nullptr;        // (Bmax)
+    float* bm_val = nullptr;        // (Bmax, nloc, NB)
+    int* bm_pos = nullptr;
+    float* row_val = nullptr;       // (Bmax, nloc)
+    int* row_pos = nullptr;
+    float* residual = nullptr;      // (Bmax, N)
+    Best* best = nullptr;           // (Bmax)
+
+    // Gram mode
+    float* gram = nullptr;          // (K, nloc, 2A)
+    float* map = nullptr;           // (Bmax, nloc, N)
+    uint64_t gram_bytes = 0;
+
+    // staging for the host-buffer entry point
+    float* d_signal = nullptr;
+    int32_t *d_atom = nullptr, *d_pos = nullptr;
+    float* d_val = nullptr;
+    size_t ev_cap = 0;
+    void* h_stage = nullptr;
+
+    std::vector<void*> allocs;
+    uint64_t bytes = 0;
+};
+
+int fail(int code, const std::string& msg);
+
+}  // namespace mpb
