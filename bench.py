@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- MP atoms/sec on BASELINE.json's headline configuration.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c1]
+
+Workload (default ``c3`` = BASELINE.json configs[2], the configuration the
+metric is quoted on): per GPU a batch of 1024 synthetic signals of 2^15
+samples, a 4096-atom x 2048-sample dictionary, 512 greedy iterations.  One
+"step" is one complete pursuit of the batch (first full correlation pass + 512
+iterations) = 524 288 atoms per GPU.  Batches shard across ranks with no
+data-path collective (weak scaling: every rank codes its own batch).
+
+Prints ONE JSON line (rank 0).  ``value`` is device-resident throughput,
+``e2e`` the same metric through the host-buffer C-ABI entry
+(mpb200_sparse_code_host: pinned host signals in, events + residual out, copies
+inside the timed region).  ``roofline`` is for the dominant kernel (the window
+re-correlation), timed live with CUDA events on its stream.  ``cpu_baseline``
+is the CPU oracle (port of the reference path) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (batch per GPU, n_samples, n_atoms, atom_size, n_steps, description)
+    "c3": (1024, 2 ** 15, 4096, 2048, 512,
+           "BASELINE configs[2]: batch 1024 x 2^15 samples, 4096-atom x 2048 dictionary, 512 iterations"),
+    "c2": (64, 2 ** 15, 512, 1024, 256,
+           "BASELINE configs[1]: batch 64 x 2^15 samples, 512-atom x 1024 dictionary, 256 iterations"),
+    "c1": (1, 2 ** 15, 512, 512, 32,
+           "BASELINE configs[0]: 1 x 2^15 samples, 512 atoms x 512 samples, 32 iterations"),
+}
+METRIC = "MP atoms/sec (4096x2048 dict, 2^15 sig)"
+UNIT = "atoms/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (marks the run non-standard)")
+    ap.add_argument("--iterations", type=int, default=0, help="override the iteration count (non-standard)")
+    ap.add_argument("--mode", default="recorrelate")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU time of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 6:
+                self.samples.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for p in self.samples:
+            try:
+                sm.append(float(p[0]))
+                mx = float(p[1])
+            except ValueError:
+                continue
+            for name, flag in zip(names, p[2:6]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------
+# synthetic inputs
+# --------------------------------------------------------------------------
+def make_inputs(torch, mpb, dev, batch, n, k, a, n_events, seed):
+    """Planted-atom signals (SURVEY.md 8d family P), built on the device with the
+    library's own decode kernel: sum of n_events unit atoms at uniform positions,
+    amplitudes U(0.5,1), plus N(0, 0.01^2) noise, max-normed per signal."""
+    g = torch.Generator(device="cpu").manual_seed(0)
+    d = torch.zeros(k, a).uniform_(-1, 1, generator=g)
+    d_dev = mpb.unit_norm(d.to(dev))
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    ev = batch * n_events
+    atom = torch.randint(0, k, (ev,), generator=g)
+    pos = torch.randint(0, max(1, n - a + 1), (ev,), generator=g)
+    amp = torch.zeros(ev).uniform_(0.5, 1.0, generator=g)
+    rows = torch.arange(batch).repeat_interleave(n_events)
+    sig = torch.zeros(batch, n, device=dev)
+    mpb.scatter_add(sig, d_dev, atom.to(dev), rows.to(dev), pos.to(dev), amp.to(dev))
+    gd = torch.Generator(device=dev).manual_seed(seed)
+    sig += 0.01 * torch.randn(batch, n, device=dev, generator=gd)
+    sig /= sig.abs().amax(dim=-1, keepdim=True) + 1e-8
+    return d, sig
+
+
+# --------------------------------------------------------------------------
+# CPU baseline (oracle port of the reference path)
+# --------------------------------------------------------------------------
+def cpu_atoms_per_second(torch, n, k, a, budget_s, seed=1):
+    """Times the CPU oracle (a port of modules/matchingpursuit.py::sparse_code,
+    same torch kernels as the reference) on ONE signal of the workload, with
+    all host threads, for both correlation forms; returns the faster."""
+    from oracle import mp_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    d = O.make_dictionary(k, a, seed=0)
+    sig = O.make_planted_signals(d, 1, n, 16, seed=seed)
+    best, detail = 0.0, {}
+    with torch.no_grad():
+        for name, kw in (("conv1d", {}), ("fft", {"approx": n})):
+            t0 = time.perf_counter()
+            O.greedy_pursuit(sig, d, 1, **kw)                      # warm-up step, also sizes the sample
+            per_step = time.perf_counter() - t0
+            steps = int(max(2, min(64, (budget_s / 2) / max(per_step, 1e-3))))
+            t0 = time.perf_counter()
+            O.greedy_pursuit(sig, d, steps, **kw)
+            dt = time.perf_counter() - t0
+            rate = steps / dt
+            detail[name] = {"steps": steps, "seconds": round(dt, 3), "atoms_per_s": round(rate, 4)}
+            best = max(best, rate)
+    sample = (f"1 signal x {n} samples, {k}x{a} dictionary; " +
+              ", ".join(f"{nm}: {v['steps']} iterations in {v['seconds']} s" for nm, v in detail.items()) +
+              "; faster form quoted")
+    return best, cores, sample, detail
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle
+    port -- the reference is pure Python and cannot travel to the GPU box; the
+    port is pinned to it by tests/golden) on the host cores, same metric."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch, n, k, a, s, desc = WORKLOADS[args.workload]
+    from oracle import mp_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    d = O.make_dictionary(k, a, seed=0)
+    sig = O.make_planted_signals(d, 1, n, 16, seed=1)
+    kw = {"approx": n} if a >= 1024 else {}
+    iters = 2 if k * a >= 2 ** 22 else 8       # bounded sample per step
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            O.greedy_pursuit(sig, d, 1, **kw)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.greedy_pursuit(sig, d, iters, **kw)
+        dt = time.perf_counter() - t0
+    value = args.steps * iters / dt
+    sample = (f"each step = {iters} greedy iterations on 1 signal x {n} samples with the {k}x{a} dictionary "
+              f"({'FFT' if kw else 'conv1d'} correlation form, {cores} threads)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+# --------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+    import matching_pursuit_b200 as mpb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the engine has no CPU path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    batch, n, k, a, s, desc = WORKLOADS[args.workload]
+    standard = True
+    if args.batch:
+        batch, standard = args.batch, False
+    if args.iterations:
+        s, standard = args.iterations, False
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json)") if peaks.get("hbm_gbs") else \
+        (6650.0, "fallback (B200_PROFILING.md)")
+
+    t_setup = time.perf_counter()
+    d, sig = make_inputs(torch, mpb, dev, batch, n, k, a, n_events=min(s, 256), seed=1 + rank)
+    plan = mpb.Plan(k, a, n, batch, mode=args.mode, device=dev)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    plan.set_dictionary(d)
+    torch.cuda.synchronize()
+    dict_ms = 1e3 * (time.perf_counter() - t0)
+    setup_s = time.perf_counter() - t_setup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput -------------------------------------
+    for _ in range(args.warmup):
+        plan.sparse_code(sig, s, want_residual=True)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    plan.timing(True)
+    launches0 = mpb.lib().mpb200_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        out = plan.sparse_code(sig, s, want_residual=True)
+    ev1.record()
+    barrier()
+    launches = mpb.lib().mpb200_launch_count() - launches0
+    ms_total = ev0.elapsed_time(ev1)
+    kernel_times = plan.timing_read()
+    plan.timing(False)
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    atoms_per_step = batch * s * world
+    value = atoms_per_step * args.steps / (ms_total / 1e3)
+
+    # ---- end to end through the host-buffer C-ABI entry ------------------
+    e2e = None
+    if not args.no_e2e:
+        sig_host = sig.cpu().pin_memory()
+        outs = (torch.empty(batch, s, dtype=torch.int32).pin_memory(),
+                torch.empty(batch, s, dtype=torch.int32).pin_memory(),
+                torch.empty(batch, s, dtype=torch.float32).pin_memory(),
+                torch.empty(batch, n, dtype=torch.float32).pin_memory())
+        plan.sparse_code_host(sig_host, s, out=outs)          # warm-up (allocates staging)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            plan.sparse_code_host(sig_host, s, out=outs)
+        e1.record()
+        barrier()
+        te = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        h2d = sig_host.numel() * 4
+        d2h = sum(o.numel() * 4 for o in outs)
+        e2e = {"value": atoms_per_step * args.steps / (float(te.item()) / 1e3), "unit": UNIT,
+               "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+               "api": "mpb200_sparse_code_host (Plan.sparse_code_host), pinned host buffers"}
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ---------------------------------
+    info = plan.info
+    m_fft, blk, nb = info.fft_size, info.block, info.n_blocks
+    corr_ms, corr_n = kernel_times["recorrelate"]
+    apply_ms, apply_n = kernel_times["apply"]
+    first_ms, first_n = kernel_times["first_pass"]
+    nvb = (2 * a - 2) // blk + 2                        # blocks refreshed per winner (worst case)
+    # algorithmic bytes of ONE re-correlation launch (one iteration of the whole batch), SURVEY.md 8(d):
+    #   pair spectra streamed once (shared by all signals)      8 * (K/2) * M
+    #   window spectra of the batch                              8 * B * M
+    #   refreshed block maxima (value + position)                8 * B * K * nvb
+    #   row re-reduction over the block-max table                4 * B * K * NB  (+ 8 * B * K written)
+    alg_bytes = 8 * ((k + 1) // 2) * m_fft + 8 * batch * m_fft + 8 * batch * k * nvb + 4 * batch * k * nb \
+        + 8 * batch * k
+    roofline = None
+    if corr_n:
+        per_launch_s = corr_ms / corr_n / 1e3
+        achieved = alg_bytes / per_launch_s / 1e9
+        flops = batch * ((k + 1) // 2) * 5.0 * m_fft * (m_fft.bit_length() - 1)   # 5 M log2 M per complex IFFT
+        roofline = {"bound": "hbm", "kernel": "k_corr (window re-correlation: fused spectrum product + inverse FFT "
+                                              "+ block/row maxima)",
+                    "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "peak_source": peak_src, "traffic": None,
+                    "alg_bytes_per_launch": alg_bytes, "ms_per_launch": corr_ms / corr_n,
+                    "share_of_step": corr_ms / ms_total,
+                    "fp32": {"note": "the kernel is FP32-pipe bound, not HBM bound: nominal 5*M*log2(M) FLOP per "
+                                     "inverse transform against the nominal (unmeasured) FP32 FMA peak",
+                             "achieved_tflops": flops / per_launch_s / 1e12,
+                             "nominal_peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12}}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic (planted atoms + noise, seeded; dictionary U(-1,1) unit-normed)",
+        "config": {"workload": desc if standard else f"NON-STANDARD batch={batch} iterations={s} of: {desc}",
+                   "batch_per_gpu": batch, "n_samples": n, "n_atoms": k, "atom_size": a, "iterations": s,
+                   "mode": plan.mode, "fft_size": m_fft, "block": blk,
+                   "parallelism": f"batch-sharded x{world}, no collective",
+                   "l2": "inputs larger than L2 (signals 128 MiB + pair spectra 128 MiB + block-max table 4 GiB "
+                         "per pass)" if standard else "working set as configured"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "kernel_ms": {"first_pass": first_ms / max(first_n, 1), "apply_per_iteration": apply_ms / max(apply_n, 1),
+                      "recorrelate_per_iteration": corr_ms / max(corr_n, 1)},
+        "setup": {"dictionary_tables_ms": dict_ms, "inputs_and_plan_s": setup_s,
+                  "plan_device_bytes": int(plan.device_bytes)},
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if roofline is not None:
+        line["roofline"] = roofline
+    if not args.no_cpu_baseline and world == 1:
+        v, cores, sample, detail = cpu_atoms_per_second(torch, n, k, a, args.cpu_seconds)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -62,6 +62,9 @@ typedef struct mpb200_best {
 
 int mpb200_version(void);
 const char* mpb200_last_error(void);
+/* Number of CUDA kernels this library has launched in this process (monotonic;
+ * benchmark bookkeeping, no reference counterpart). */
+unsigned long long mpb200_launch_count(void);
 
 /* Plan: sizes workspaces for signals of n_samples, batches up to max_batch and
  * a dictionary of n_atoms x atom_size of which this plan owns atoms
@@ -73,6 +76,16 @@ int mpb200_plan_create(mpb200_plan_t* plan, int n_atoms, int atom_size, int n_sa
                        int mode, int atom_lo, int atom_hi, uint64_t gram_budget_bytes);
 int mpb200_plan_destroy(mpb200_plan_t plan);
 int mpb200_plan_info_get(mpb200_plan_t plan, mpb200_plan_info* info);
+
+/* Per-kernel device timing of the pursuit loop (bench / profiling aid, no
+ * reference counterpart).  While enabled, mpb200_sparse_code records a CUDA
+ * event on `stream` after the first full pass and after every apply and
+ * re-correlation launch.  mpb200_plan_timing_read waits for the last event and
+ * returns, for tag 1 = first pass, 2 = select+subtract+window FFT ("apply"),
+ * 3 = window re-correlation + block/row maxima, the accumulated milliseconds
+ * and number of intervals since the previous read (arrays of 4; index 0 unused). */
+int mpb200_plan_timing_enable(mpb200_plan_t plan, int enable);
+int mpb200_plan_timing_read(mpb200_plan_t plan, double* ms_by_tag, int64_t* count_by_tag);
 
 /* Dictionary: d is (n_atoms, atom_size) row-major.  The plan keeps
  * x / (||x||_2 + 1e-8) per row -- modules/normalization.py:4-6, applied by the
@@ -126,14 +139,45 @@ int mpb200_residual(mpb200_plan_t plan, float* residual_out, void* stream);
  * all-gather of mpb200_local_best records. */
 int mpb200_reduce_best(const mpb200_best* cand, int n_ranks, int batch, mpb200_best* winner, void* stream);
 
+/* Selection on a DENSE map fm (batch, n_atoms, n_samples) that the caller
+ * already holds (a `compute_feature_map` callback result, or
+ * mpb200_correlate output handed to a per-step visitor): signed maximum per
+ * signal, first flat index on ties -- torch.max over fm.reshape(batch, -1) at
+ * modules/matchingpursuit.py:298-303; also the top-1 of sparsify2,
+ * modules/sparse.py:64.  best[b].atom = atom_offset + row of the maximum. */
+int mpb200_select_dense(const float* fm, int batch, int n_atoms, int n_samples, int atom_offset,
+                        mpb200_best* best, void* stream);
+/* Same, with the reference's opt-in local contrast normalisation: the argmax
+ * runs on fm - avg_pool2d(fm, (9,9), stride 1, zero padding 4) over the
+ * (atom, time) plane and the reported value is the RAW map value at that
+ * index -- modules/matchingpursuit.py:286-296. */
+int mpb200_select_lcn(const float* fm, int batch, int n_atoms, int n_samples, int atom_offset,
+                      mpb200_best* best, void* stream);
+/* residual[b, p : p+atom_size] -= winner[b].value * d_unit[winner[b].atom],
+ * p = winner[b].position, truncated at the right edge -- the residual update
+ * of modules/matchingpursuit.py:326-328 (and :108-120). */
+int mpb200_subtract(float* residual, int batch, int n_samples, const float* d_unit, int n_atoms, int atom_size,
+                    const mpb200_best* winner, void* stream);
+
 /* Decode: out[b, pos : pos+atom_size] += val * d_unit[atom], truncated at the
  * right edge -- replaces scatter_segments, modules/matchingpursuit.py:20-58
  * (single-channel branch :48).  out is (batch, n_samples) and is accumulated
  * into (zero it first for a fresh decode).  Events: n_events entries of
- * (atom, batch index, position, value). */
+ * (atom, batch index, position, value), summed in list order per sample.
+ * row_offsets: NULL, or batch+1 offsets when the events are sorted by batch
+ * index (events of signal b are [row_offsets[b], row_offsets[b+1])). */
 int mpb200_scatter_add(float* out, int batch, int n_samples, const float* d_unit, int n_atoms, int atom_size,
                        const int32_t* atom, const int32_t* batch_index, const int32_t* pos, const float* val,
-                       int n_events, void* stream);
+                       const int32_t* row_offsets, int n_events, void* stream);
+/* Same with caller-supplied scaled atoms: out[row_index[e], pos[e] : +atom_size] += rows[e, :]
+ * (rows is (n_events, atom_size)) -- scatter_segments fed with arbitrary event
+ * tuples (modules/matchingpursuit.py:41-52, used by dictionary_learning_step
+ * :408-415 and BandSpec.decode, modules/multibanddict.py:265-266).  out is
+ * (n_rows, n_samples); for the reference's one-channel-per-event mode (:50) the
+ * caller passes row = batch * channels + channel. */
+int mpb200_scatter_rows(float* out, int n_rows, int n_samples, const float* rows, int atom_size,
+                        const int32_t* row_index, const int32_t* pos, const int32_t* row_offsets, int n_events,
+                        void* stream);
 /* scaled[e, :] = val[e] * d_unit[atom[e], :]  -- the `a` member of the
  * reference's event tuples (modules/matchingpursuit.py:305, 315). */
 int mpb200_gather_atoms(float* scaled, const float* d_unit, int n_atoms, int atom_size,

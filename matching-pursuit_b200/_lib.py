@@ -63,9 +63,12 @@ _i = C.c_int
 _SIGNATURES = {
     "mpb200_version": (C.c_int, []),
     "mpb200_last_error": (C.c_char_p, []),
+    "mpb200_launch_count": (C.c_ulonglong, []),
     "mpb200_plan_create": (_i, [C.POINTER(_p), _i, _i, _i, _i, _i, _i, _i, C.c_uint64]),
     "mpb200_plan_destroy": (_i, [_p]),
     "mpb200_plan_info_get": (_i, [_p, C.POINTER(PlanInfo)]),
+    "mpb200_plan_timing_enable": (_i, [_p, _i]),
+    "mpb200_plan_timing_read": (_i, [_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "mpb200_plan_set_dictionary": (_i, [_p, _p, _p]),
     "mpb200_plan_get_unit_dictionary": (_i, [_p, _p, _p]),
     "mpb200_sparse_code": (_i, [_p, _p, _i, _i, _p, _p, _p, _p, _p]),
@@ -76,8 +79,11 @@ _SIGNATURES = {
     "mpb200_apply": (_i, [_p, _p, _p]),
     "mpb200_residual": (_i, [_p, _p, _p]),
     "mpb200_reduce_best": (_i, [_p, _i, _i, _p, _p]),
-    "mpb200_scatter_add": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _i, _p]),
-    "mpb200_scatter_rows": (_i, [_p, _i, _i, _p, _i, _p, _p, _i, _p]),
+    "mpb200_scatter_add": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p, _i, _p]),
+    "mpb200_scatter_rows": (_i, [_p, _i, _i, _p, _i, _p, _p, _p, _i, _p]),
+    "mpb200_select_dense": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    "mpb200_select_lcn": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    "mpb200_subtract": (_i, [_p, _i, _i, _p, _i, _i, _p, _p]),
     "mpb200_gather_atoms": (_i, [_p, _p, _i, _i, _p, _p, _i, _p]),
     "mpb200_unit_norm": (_i, [_p, _p, _i, _i, C.c_float, _p]),
     "mpb200_fft_convolve": (_i, [_p, _i, _p, _i, _i, _i, _p, _p]),

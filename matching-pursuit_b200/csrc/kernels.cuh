@@ -477,15 +477,144 @@ k_apply(const ApplyArgs a) {
 }
 
 // ---------------------------------------------------------------------------
+// Selection on a dense map (B, K, N) the caller holds.  grid = (G, B): CTA g of
+// signal b scans map rows g, g+G, ... with 128-bit loads and writes one
+// candidate to part[g*B + b] (rank-major, the layout k_reduce_best takes).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void take_better3(float& v, int& k, int& t, float ov, int ok, int ot) {
+    if (ov > v || (ov == v && (ok < k || (ok == k && ot < t)))) {
+        v = ov;
+        k = ok;
+        t = ot;
+    }
+}
+
+// LCN: the selection runs on fm - avg_pool2d(fm, 9x9, stride 1, zero padding 4) over the
+// (atom, time) plane (modules/matchingpursuit.py:286-292); the candidate carries the
+// normalised value, k_finish_best swaps in the raw one (:296).
+template <bool LCN>
+__device__ __forceinline__ float selection_value(const float* __restrict__ base, int K, int N, int k, int t) {
+    const float c = base[(size_t)k * N + t];
+    if constexpr (!LCN) {
+        return c;
+    } else {
+        float s = 0.f;
+#pragma unroll 1
+        for (int dk = -4; dk <= 4; ++dk) {
+            const int kk = k + dk;
+            if (kk < 0 || kk >= K) continue;
+            const float* __restrict__ row = base + (size_t)kk * N;
+#pragma unroll
+            for (int dt = -4; dt <= 4; ++dt) {
+                const int tt = t + dt;
+                if (tt >= 0 && tt < N) s = __fadd_rn(s, __ldg(row + tt));
+            }
+        }
+        return __fsub_rn(c, __fdiv_rn(s, 81.f));
+    }
+}
+
+template <bool LCN>
+__global__ void __launch_bounds__(256)
+k_select_dense(const float* __restrict__ fm, int K, int N, int atom_offset, Best* __restrict__ part) {
+    const int b = blockIdx.y, B = gridDim.y;
+    const float* __restrict__ base = fm + (size_t)b * K * N;
+    float v = -INFINITY;
+    int bk = INT_MAX, bt = INT_MAX;
+    const bool vec = !LCN && (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(fm) & 15) == 0);
+    for (int k = blockIdx.x; k < K; k += gridDim.x) {
+        const float* __restrict__ row = base + (size_t)k * N;
+        if (vec) {
+            const float4* __restrict__ row4 = reinterpret_cast<const float4*>(row);
+            for (int i = threadIdx.x; i < N / 4; i += blockDim.x) {
+                const float4 c = __ldg(row4 + i);
+                // ascending t inside the thread: strict > keeps the first maximum
+                if (c.x > v) { v = c.x; bk = k; bt = 4 * i; }
+                if (c.y > v) { v = c.y; bk = k; bt = 4 * i + 1; }
+                if (c.z > v) { v = c.z; bk = k; bt = 4 * i + 2; }
+                if (c.w > v) { v = c.w; bk = k; bt = 4 * i + 3; }
+            }
+        } else {
+            for (int t = threadIdx.x; t < N; t += blockDim.x) {
+                const float c = selection_value<LCN>(base, K, N, k, t);
+                if (c > v) { v = c; bk = k; bt = t; }
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, off);
+        const int ok = __shfl_xor_sync(0xffffffffu, bk, off);
+        const int ot = __shfl_xor_sync(0xffffffffu, bt, off);
+        take_better3(v, bk, bt, ov, ok, ot);
+    }
+    __shared__ float s_v[8];
+    __shared__ int s_k[8], s_t[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { s_v[warp] = v; s_k[warp] = bk; s_t[warp] = bt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) take_better3(v, bk, bt, s_v[w], s_k[w], s_t[w]);
+        Best r;
+        if (bk == INT_MAX) {   // nothing compared greater than -inf (all NaN / -inf)
+            r.value = -INFINITY;
+            r.atom = INT_MAX;  // loses every tie-break in k_reduce_best
+            r.position = INT_MAX;
+        } else {
+            r.value = v;
+            r.atom = bk;       // local row; k_finish_best adds atom_offset
+            r.position = bt;
+        }
+        r.pad = 0;
+        part[(size_t)blockIdx.x * B + b] = r;
+    }
+}
+
+// After k_reduce_best on k_select_dense candidates: a signal whose map held no
+// value above -inf gets row 0, position 0; the value becomes the RAW map value at
+// the winner (identical to the candidate's unless LCN); atom_offset is applied.
+__global__ void k_finish_best(Best* __restrict__ best, int batch, const float* __restrict__ fm, int K, int N,
+                              int atom_offset) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    Best r = best[b];
+    if (r.atom == INT_MAX) {
+        r.atom = 0;
+        r.position = 0;
+    }
+    r.value = fm[((size_t)b * K + r.atom) * N + r.position];
+    r.atom += atom_offset;
+    best[b] = r;
+}
+
+// residual[b, p:p+A] -= value * dict[atom]  (fl(r - fl(v*d)), truncated at the right edge).
+// grid = batch, 256 threads.
+__global__ void __launch_bounds__(256)
+k_subtract(float* __restrict__ residual, int N, const float* __restrict__ dict, int K, int A,
+           const Best* __restrict__ winner) {
+    const int b = blockIdx.x;
+    const Best w = winner[b];
+    if (w.atom < 0 || w.atom >= K || w.position < 0 || w.position >= N) return;
+    float* __restrict__ r = residual + (size_t)b * N + w.position;
+    const float* __restrict__ d = dict + (size_t)w.atom * A;
+    const int keep = min(A, N - w.position);
+    for (int i = threadIdx.x; i < keep; i += blockDim.x) r[i] = __fsub_rn(r[i], __fmul_rn(w.value, d[i]));
+}
+
+// ---------------------------------------------------------------------------
 // Decode helpers (modules/matchingpursuit.py:20-58, :305).
 // ---------------------------------------------------------------------------
 // Deterministic: a thread owns output samples and walks the events in list
 // order, so overlapping atoms are summed in the reference's order.
-// grid = (ceil(N / 1024), batch), 256 threads, 4 samples per thread.
+//   out[row_index[e], pos[e] + i] += scale[e] * src[src_index[e], i],  i < A, truncated at N
+// src_index == null -> row e of src; scale == null -> 1 (adds src rows as they are).
+// row_offsets (n_rows + 1 entries) says the events are sorted by row and which
+// range belongs to each row; without it every CTA filters the whole list.
+// grid = (ceil(N / 1024), n_rows), 256 threads, 4 samples per thread.
 __global__ void __launch_bounds__(256)
-k_scatter_add(float* __restrict__ out, int batch, int N, const float* __restrict__ dict, int K, int A,
-              const int* __restrict__ atom, const int* __restrict__ bidx, const int* __restrict__ pos,
-              const float* __restrict__ val, int n_events) {
+k_scatter(float* __restrict__ out, int N, const float* __restrict__ src, int n_src, int A,
+          const int* __restrict__ src_index, const int* __restrict__ row_index, const int* __restrict__ pos,
+          const float* __restrict__ scale, const int* __restrict__ row_offsets, int n_events) {
     const int b = blockIdx.y;
     const int tile0 = blockIdx.x * 1024;
     float acc[4];
@@ -495,12 +624,15 @@ k_scatter_add(float* __restrict__ out, int batch, int N, const float* __restrict
         t[u] = tile0 + threadIdx.x + 256 * u;
         acc[u] = t[u] < N ? out[(size_t)b * N + t[u]] : 0.f;
     }
-    for (int e = 0; e < n_events; ++e) {
-        if (bidx[e] != b) continue;
-        const int p = pos[e], k = atom[e];
-        if (k < 0 || k >= K || p + A <= tile0 || p >= tile0 + 1024 || p < 0) continue;
-        const float v = val[e];
-        const float* d = dict + (size_t)k * A;
+    const int e0 = row_offsets ? row_offsets[b] : 0;
+    const int e1 = row_offsets ? row_offsets[b + 1] : n_events;
+    for (int e = e0; e < e1; ++e) {
+        if (row_index[e] != b) continue;
+        const int p = pos[e];
+        const int k = src_index ? src_index[e] : e;
+        if (k < 0 || k >= n_src || p + A <= tile0 || p >= tile0 + 1024 || p < 0) continue;
+        const float v = scale ? scale[e] : 1.f;
+        const float* d = src + (size_t)k * A;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int i = t[u] - p;

@@ -2,6 +2,7 @@
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
 //             -Xcompiler -fPIC -shared -o libmpb200.so mpb200.cu fftconv.cu
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -15,6 +16,7 @@
 namespace mpb {
 
 thread_local std::string g_last_error;
+std::atomic<unsigned long long> g_launches{0};   // kernels launched by this library (process-wide)
 
 int fail(int code, const std::string& msg) {
     g_last_error = msg;
@@ -30,6 +32,7 @@ int fail(int code, const std::string& msg) {
 
 #define MPB_LAUNCH_CHECK(name)                                                                  \
     do {                                                                                        \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                     \
         cudaError_t _e = cudaGetLastError();                                                    \
         if (_e != cudaSuccess)                                                                  \
             return fail(MPB200_ECUDA, std::string("launch ") + name + ": " + cudaGetErrorString(_e)); \
@@ -96,6 +99,7 @@ static int dev_alloc(Plan* p, T** ptr, size_t count) {
 }
 
 static void free_plan(Plan* p) {
+    for (void* e : p->ev_pool) cudaEventDestroy((cudaEvent_t)e);
     for (void* q : p->allocs) cudaFree(q);
     if (p->h_stage) cudaFreeHost(p->h_stage);
     delete p;
@@ -253,6 +257,18 @@ static int build_pair_spectra(Plan* p, cudaStream_t st) {
     return MPB200_OK;
 }
 
+// timing marker: everything enqueued on `st` since the previous marker is attributed to `tag`
+static void mark(Plan* p, int tag, cudaStream_t st) {
+    if (!p->timing) return;
+    if (p->ev_used == p->ev_pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return; }
+        p->ev_pool.push_back((void*)e);
+    }
+    cudaEventRecord((cudaEvent_t)p->ev_pool[p->ev_used++], st);
+    p->ev_tag.push_back(tag);
+}
+
 static int check_plan(Plan* p, bool need_dict) {
     if (!p) return fail(MPB200_EINVAL, "null plan");
     if (need_dict && !p->dict_set) return fail(MPB200_ESTATE, "mpb200_plan_set_dictionary has not been called");
@@ -270,6 +286,8 @@ extern "C" {
 int mpb200_version(void) { return MPB200_VERSION; }
 
 const char* mpb200_last_error(void) { return g_last_error.c_str(); }
+
+unsigned long long mpb200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int mpb200_plan_create(mpb200_plan_t* out, int n_atoms, int atom_size, int n_samples, int max_batch, int mode,
                        int atom_lo, int atom_hi, uint64_t gram_budget_bytes) {
@@ -407,6 +425,33 @@ int mpb200_plan_info_get(mpb200_plan_t plan, mpb200_plan_info* info) {
     return MPB200_OK;
 }
 
+int mpb200_plan_timing_enable(mpb200_plan_t plan, int enable) {
+    Plan* p = reinterpret_cast<Plan*>(plan);
+    if (!p) return fail(MPB200_EINVAL, "null plan");
+    p->timing = enable != 0;
+    p->ev_used = 0;
+    p->ev_tag.clear();
+    return MPB200_OK;
+}
+
+int mpb200_plan_timing_read(mpb200_plan_t plan, double* ms_by_tag, int64_t* count_by_tag) {
+    Plan* p = reinterpret_cast<Plan*>(plan);
+    if (!p || !ms_by_tag || !count_by_tag) return fail(MPB200_EINVAL, "null argument");
+    for (int t = 0; t < 4; ++t) { ms_by_tag[t] = 0.0; count_by_tag[t] = 0; }
+    if (p->ev_used) MPB_CUDA(cudaEventSynchronize((cudaEvent_t)p->ev_pool[p->ev_used - 1]));
+    for (size_t i = 1; i < p->ev_used; ++i) {
+        const int tag = p->ev_tag[i];
+        if (tag == 0) continue;   // a start marker opens a new call; the gap before it is not ours
+        float ms = 0.f;
+        MPB_CUDA(cudaEventElapsedTime(&ms, (cudaEvent_t)p->ev_pool[i - 1], (cudaEvent_t)p->ev_pool[i]));
+        ms_by_tag[tag] += ms;
+        count_by_tag[tag] += 1;
+    }
+    p->ev_used = 0;
+    p->ev_tag.clear();
+    return MPB200_OK;
+}
+
 int mpb200_plan_set_dictionary(mpb200_plan_t plan, const float* d, void* stream) {
     Plan* p = reinterpret_cast<Plan*>(plan);
     int rc = check_plan(p, false);
@@ -492,17 +537,21 @@ int mpb200_sparse_code(mpb200_plan_t plan, const float* signal, int batch, int n
     if (p && (p->lo != 0 || p->hi != p->K))
         return fail(MPB200_ESTATE, "mpb200_sparse_code needs a plan that owns every atom; "
                                    "sharded plans use begin/local_best/apply");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p) mark(p, 0, st);
     int rc = mpb200_begin(plan, signal, batch, stream);
     if (rc) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
+    mark(p, 1, st);
     for (int s = 0; s < n_steps; ++s) {
         const bool last = (s == n_steps - 1);
         rc = launch_apply<true>(p, batch, nullptr, s, n_steps, atom_out, pos_out, val_out,
                                 (!last && p->mode != MPB200_MODE_FULL) ? 1 : 0, st);
         if (rc) return rc;
+        mark(p, 2, st);
         if (!last) {
             rc = step_refresh(p, batch, st);
             if (rc) return rc;
+            mark(p, 3, st);
         }
     }
     if (n_steps > 0) p->cur_batch = 0;  // block maxima are stale after the last subtraction
@@ -561,17 +610,96 @@ int mpb200_correlate(mpb200_plan_t plan, const float* signal, int batch, float* 
     return full_pass(p, batch, fm_out, st);
 }
 
+// Scratch for k_select_dense partial winners: one growing buffer per device (never shrinks;
+// stream-ordered reuse is safe because consecutive calls on different streams are the
+// caller's to order, as with any workspace-free entry point).
+static Best* g_sel_scratch[64] = {nullptr};
+static size_t g_sel_cap[64] = {0};
+
+static int select_dense_impl(const float* fm, int batch, int n_atoms, int n_samples, int atom_offset,
+                             mpb200_best* best, bool lcn, void* stream) {
+    if (!fm || !best || batch < 1 || n_atoms < 1 || n_samples < 1) return fail(MPB200_EINVAL, "bad argument");
+    int dev = 0;
+    MPB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(MPB200_EINVAL, "device index out of range");
+    int sms = 148;
+    MPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int G = (sms * 8 + batch - 1) / batch;   // CTAs per signal: fill the chip ~8 deep
+    if (G > n_atoms) G = n_atoms;
+    if (G < 1) G = 1;
+    const size_t need = (size_t)G * batch;
+    if (need > g_sel_cap[dev]) {
+        if (g_sel_scratch[dev]) {
+            MPB_CUDA(cudaDeviceSynchronize());
+            cudaFree(g_sel_scratch[dev]);
+            g_sel_scratch[dev] = nullptr;
+            g_sel_cap[dev] = 0;
+        }
+        cudaError_t e = cudaMalloc((void**)&g_sel_scratch[dev], need * sizeof(Best));
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(MPB200_ENOMEM, std::string("select scratch: ") + cudaGetErrorString(e));
+        }
+        g_sel_cap[dev] = need;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    Best* part = g_sel_scratch[dev];
+    if (lcn) k_select_dense<true><<<dim3(G, batch), 256, 0, st>>>(fm, n_atoms, n_samples, atom_offset, part);
+    else k_select_dense<false><<<dim3(G, batch), 256, 0, st>>>(fm, n_atoms, n_samples, atom_offset, part);
+    MPB_LAUNCH_CHECK("k_select_dense");
+    k_reduce_best<<<(batch + 127) / 128, 128, 0, st>>>(part, G, batch, reinterpret_cast<Best*>(best));
+    MPB_LAUNCH_CHECK("k_reduce_best");
+    k_finish_best<<<(batch + 127) / 128, 128, 0, st>>>(reinterpret_cast<Best*>(best), batch, fm, n_atoms, n_samples,
+                                                       atom_offset);
+    MPB_LAUNCH_CHECK("k_finish_best");
+    return MPB200_OK;
+}
+
+int mpb200_select_dense(const float* fm, int batch, int n_atoms, int n_samples, int atom_offset, mpb200_best* best,
+                        void* stream) {
+    return select_dense_impl(fm, batch, n_atoms, n_samples, atom_offset, best, false, stream);
+}
+
+int mpb200_select_lcn(const float* fm, int batch, int n_atoms, int n_samples, int atom_offset, mpb200_best* best,
+                      void* stream) {
+    return select_dense_impl(fm, batch, n_atoms, n_samples, atom_offset, best, true, stream);
+}
+
+int mpb200_subtract(float* residual, int batch, int n_samples, const float* d_unit, int n_atoms, int atom_size,
+                    const mpb200_best* winner, void* stream) {
+    if (!residual || !d_unit || !winner || batch < 1 || n_samples < 1 || n_atoms < 1 || atom_size < 1)
+        return fail(MPB200_EINVAL, "bad argument");
+    k_subtract<<<batch, 256, 0, (cudaStream_t)stream>>>(residual, n_samples, d_unit, n_atoms, atom_size,
+                                                        reinterpret_cast<const Best*>(winner));
+    MPB_LAUNCH_CHECK("k_subtract");
+    return MPB200_OK;
+}
+
 int mpb200_scatter_add(float* out, int batch, int n_samples, const float* d_unit, int n_atoms, int atom_size,
                        const int32_t* atom, const int32_t* batch_index, const int32_t* pos, const float* val,
-                       int n_events, void* stream) {
+                       const int32_t* row_offsets, int n_events, void* stream) {
     if (!out || !d_unit || batch < 1 || n_samples < 1 || n_atoms < 1 || atom_size < 1 || n_events < 0)
         return fail(MPB200_EINVAL, "bad argument");
     if (n_events == 0) return MPB200_OK;
     if (!atom || !batch_index || !pos || !val) return fail(MPB200_EINVAL, "null event array");
     dim3 grid((n_samples + 1023) / 1024, batch);
-    k_scatter_add<<<grid, 256, 0, (cudaStream_t)stream>>>(out, batch, n_samples, d_unit, n_atoms, atom_size, atom,
-                                                          batch_index, pos, val, n_events);
-    MPB_LAUNCH_CHECK("k_scatter_add");
+    k_scatter<<<grid, 256, 0, (cudaStream_t)stream>>>(out, n_samples, d_unit, n_atoms, atom_size, atom, batch_index,
+                                                      pos, val, row_offsets, n_events);
+    MPB_LAUNCH_CHECK("k_scatter");
+    return MPB200_OK;
+}
+
+int mpb200_scatter_rows(float* out, int n_rows, int n_samples, const float* rows, int atom_size,
+                        const int32_t* row_index, const int32_t* pos, const int32_t* row_offsets, int n_events,
+                        void* stream) {
+    if (!out || n_rows < 1 || n_samples < 1 || atom_size < 1 || n_events < 0)
+        return fail(MPB200_EINVAL, "bad argument");
+    if (n_events == 0) return MPB200_OK;
+    if (!rows || !row_index || !pos) return fail(MPB200_EINVAL, "null event array");
+    dim3 grid((n_samples + 1023) / 1024, n_rows);
+    k_scatter<<<grid, 256, 0, (cudaStream_t)stream>>>(out, n_samples, rows, n_events, atom_size, nullptr, row_index,
+                                                      pos, nullptr, row_offsets, n_events);
+    MPB_LAUNCH_CHECK("k_scatter");
     return MPB200_OK;
 }
 

@@ -45,6 +45,13 @@ struct Plan {
     size_t ev_cap = 0;
     void* h_stage = nullptr;
 
+    // optional per-kernel timing (bench aid): consecutive events on the caller's stream, tagged
+    // with what ran since the previous one (0 = start marker, 1 = first pass, 2 = apply, 3 = re-correlation)
+    bool timing = false;
+    std::vector<void*> ev_pool;         // cudaEvent_t
+    std::vector<int> ev_tag;            // tags of the events recorded since the last read
+    size_t ev_used = 0;
+
     std::vector<void*> allocs;
     uint64_t bytes = 0;
 };

@@ -1,0 +1,306 @@
+"""Thin torch-side wrapper of an ``mpb200_plan_t`` (include/mpb200.h).
+
+PyTorch is plumbing here: it owns device buffers and the current CUDA stream;
+every computation is a call through the C ABI into the sm_100a kernels.  There
+is no CPU path -- constructing a :class:`Plan` without the built library or
+without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import MODES, MODE_NAMES, MpbError, PlanInfo, check, lib
+
+
+def _stream_ptr(device: torch.device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise MpbError("no CUDA device: matching-pursuit_b200 has no CPU path")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.type != "cuda":
+        raise MpbError(f"device must be a CUDA device, got {dev}")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def _dev_f32(x: torch.Tensor, device: torch.device, shape=None) -> torch.Tensor:
+    x = x.detach()
+    if x.dtype != torch.float32 or x.device != device or not x.is_contiguous():
+        x = x.to(device=device, dtype=torch.float32).contiguous()
+    return x if shape is None else x.view(*shape)
+
+
+class Plan:
+    """Workspaces + derived dictionary tables for signals of ``n_samples``,
+    batches up to ``max_batch`` and a ``(n_atoms, atom_size)`` dictionary of
+    which this plan owns atoms ``[atom_lo, atom_hi)``."""
+
+    def __init__(self, n_atoms: int, atom_size: int, n_samples: int, max_batch: int, mode: str = "auto",
+                 atom_range: Optional[Tuple[int, int]] = None, device=None, gram_budget_bytes: int = 0):
+        self.device = _require_cuda(device)
+        self._lib = lib()
+        lo, hi = (0, n_atoms) if atom_range is None else atom_range
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self._lib.mpb200_plan_create(C.byref(self._h), n_atoms, atom_size, n_samples, max_batch,
+                                               MODES[mode] if isinstance(mode, str) else int(mode), lo, hi,
+                                               C.c_uint64(gram_budget_bytes)), "mpb200_plan_create")
+        self._finalizer = weakref.finalize(self, Plan._destroy, self._lib, self._h)
+        info = PlanInfo()
+        check(self._lib.mpb200_plan_info_get(self._h, C.byref(info)), "mpb200_plan_info_get")
+        self.info = info
+        self.n_atoms, self.atom_size, self.n_samples, self.max_batch = n_atoms, atom_size, n_samples, max_batch
+        self.atom_lo, self.atom_hi = info.atom_lo, info.atom_hi
+        self.mode = MODE_NAMES[info.mode]
+        self.fft_size, self.block, self.n_blocks = info.fft_size, info.block, info.n_blocks
+        self.device_bytes = info.device_bytes
+        self.batch = 0
+        self.dictionary_key = None   # set by callers that cache plans
+
+    @staticmethod
+    def _destroy(library, handle):
+        if handle:
+            library.mpb200_plan_destroy(handle)
+
+    def close(self):
+        self._finalizer()
+
+    # ---- per-kernel timing (bench aid) ----------------------------------
+    def timing(self, enable: bool) -> None:
+        check(self._lib.mpb200_plan_timing_enable(self._h, int(bool(enable))), "mpb200_plan_timing_enable")
+
+    def timing_read(self) -> dict:
+        """{'first_pass'|'apply'|'recorrelate': (milliseconds, intervals)} since the last read."""
+        ms = (C.c_double * 4)()
+        cnt = (C.c_int64 * 4)()
+        with torch.cuda.device(self.device):
+            check(self._lib.mpb200_plan_timing_read(self._h, ms, cnt), "mpb200_plan_timing_read")
+        return {"first_pass": (ms[1], cnt[1]), "apply": (ms[2], cnt[2]), "recorrelate": (ms[3], cnt[3])}
+
+    # ---- dictionary -----------------------------------------------------
+    def set_dictionary(self, d: torch.Tensor) -> "Plan":
+        """``d`` is (K, A) (or (K, 1, A)); it is unit-normed on the device
+        exactly like modules/normalization.py:4-6 and not modified."""
+        d = _dev_f32(d, self.device).reshape(d.shape[0], -1)
+        if tuple(d.shape) != (self.n_atoms, self.atom_size):
+            raise MpbError(f"dictionary shape {tuple(d.shape)} does not match the plan "
+                           f"({self.n_atoms}, {self.atom_size})")
+        with torch.cuda.device(self.device):
+            check(self._lib.mpb200_plan_set_dictionary(self._h, _ptr(d), _stream_ptr(self.device)),
+                  "mpb200_plan_set_dictionary")
+        self._keep = d  # stream-ordered use: keep alive until the next call replaces it
+        return self
+
+    def unit_dictionary(self) -> torch.Tensor:
+        out = torch.empty(self.n_atoms, self.atom_size, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(self._lib.mpb200_plan_get_unit_dictionary(self._h, _ptr(out), _stream_ptr(self.device)),
+                  "mpb200_plan_get_unit_dictionary")
+        return out
+
+    # ---- whole pursuit --------------------------------------------------
+    def _check_signal(self, signal: torch.Tensor) -> Tuple[int, torch.Tensor]:
+        b = signal.shape[0]
+        if signal.numel() != b * self.n_samples:
+            raise MpbError(f"signal of shape {tuple(signal.shape)} does not hold {self.n_samples} samples per row")
+        if not 1 <= b <= self.max_batch:
+            raise MpbError(f"batch {b} is outside [1, {self.max_batch}]")
+        return b, signal
+
+    def sparse_code(self, signal: torch.Tensor, n_steps: int, want_residual: bool = True):
+        """Device-resident pursuit.  Returns ``(atom, pos, val, residual)``:
+        int32 (B,S), int32 (B,S), float32 (B,S), float32 (B,N) or None."""
+        b, _ = self._check_signal(signal)
+        sig = _dev_f32(signal, self.device, (b, self.n_samples))
+        atom = torch.empty(b, n_steps, device=self.device, dtype=torch.int32)
+        pos = torch.empty(b, n_steps, device=self.device, dtype=torch.int32)
+        val = torch.empty(b, n_steps, device=self.device, dtype=torch.float32)
+        res = torch.empty(b, self.n_samples, device=self.device, dtype=torch.float32) if want_residual else None
+        with torch.cuda.device(self.device):
+            check(self._lib.mpb200_sparse_code(self._h, _ptr(sig), b, n_steps, _ptr(res), _ptr(atom), _ptr(pos),
+                                               _ptr(val), _stream_ptr(self.device)), "mpb200_sparse_code")
+        self.batch = 0
+        return atom, pos, val, res
+
+    def sparse_code_host(self, signal: torch.Tensor, n_steps: int, want_residual: bool = True, out=None):
+        """End-to-end entry for HOST tensors: H2D, pursuit, D2H, synchronised.
+        ``out`` may hold preallocated (pinned) ``(atom, pos, val, residual)``."""
+        b, _ = self._check_signal(signal)
+        if signal.device.type != "cpu" or signal.dtype != torch.float32 or not signal.is_contiguous():
+            signal = signal.detach().to("cpu", torch.float32).contiguous()
+        if out is None:
+            atom = torch.empty(b, n_steps, dtype=torch.int32)
+            pos = torch.empty(b, n_steps, dtype=torch.int32)
+            val = torch.empty(b, n_steps, dtype=torch.float32)
+            res = torch.empty(b, self.n_samples, dtype=torch.float32) if want_residual else None
+        else:
+            atom, pos, val, res = out
+        with torch.cuda.device(self.device):
+            check(self._lib.mpb200_sparse_code_host(self._h, _ptr(signal), b, n_steps, _ptr(res), _ptr(atom),
+                                                    _ptr(pos), _ptr(val), _stream_ptr(self.device)),
+                  "mpb200_sparse_code_host")
+        self.batch = 0
+        return atom, pos, val, res
+
+    def correlate(self, signal: torch.Tensor) -> torch.Tensor:
+        """Dense (B, owned atoms, N) correlation map of ``signal`` (B, N)."""
+        b, _ = self._check_signal(signal)
+        sig = _dev_f32(signal, self.device, (b, self.n_samples))
+        fm = torch.empty(b, self.atom_hi - self.atom_lo, self.n_samples, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(self._lib.mpb200_correlate(self._h, _ptr(sig), b, _ptr(fm), _stream_ptr(self.device)),
+                  "mpb200_correlate")
+        self.batch = 0
+        return fm
+
+    # ---- step-wise interface (atom sharding, per-step callbacks) ---------
+    def begin(self, signal: torch.Tensor) -> None:
+        b, _ = self._check_signal(signal)
+        sig = _dev_f32(signal, self.device, (b, self.n_samples))
+        with torch.cuda.device(self.device):
+            check(self._lib.mpb200_begin(self._h, _ptr(sig), b, _stream_ptr(self.device)), "mpb200_begin")
+        self.batch = b
+
+    def local_best(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """(B, 4) int32 view of ``mpb200_best`` records: value bits, atom, position, pad."""
+        if out is None:
+            out = torch.empty(self.batch, 4, device=self.device, dtype=torch.int32)
+        with torch.cuda.device(self.device):
+            check(self._lib.mpb200_local_best(self._h, _ptr(out), _stream_ptr(self.device)), "mpb200_local_best")
+        return out
+
+    def apply(self, winner: torch.Tensor) -> None:
+        with torch.cuda.device(self.device):
+            check(self._lib.mpb200_apply(self._h, _ptr(winner), _stream_ptr(self.device)), "mpb200_apply")
+
+    def residual(self) -> torch.Tensor:
+        out = torch.empty(self.batch, self.n_samples, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(self._lib.mpb200_residual(self._h, _ptr(out), _stream_ptr(self.device)), "mpb200_residual")
+        return out
+
+
+def reduce_best(cand: torch.Tensor, n_ranks: int, batch: int) -> torch.Tensor:
+    """Global winner per signal from rank-major candidates ``(n_ranks*batch, 4)`` int32."""
+    dev = cand.device
+    out = torch.empty(batch, 4, device=dev, dtype=torch.int32)
+    with torch.cuda.device(dev):
+        check(lib().mpb200_reduce_best(_ptr(cand), n_ranks, batch, _ptr(out), _stream_ptr(dev)), "mpb200_reduce_best")
+    return out
+
+
+def unpack_best(rec: torch.Tensor):
+    """(value float32, atom int32, position int32) columns of best records."""
+    return rec[:, 0].view(torch.float32), rec[:, 1], rec[:, 2]
+
+
+# ---- stateless helpers ------------------------------------------------------
+
+def unit_norm(x: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
+    """Rows of a CUDA tensor divided by (||row||_2 + eps) -- modules/normalization.py:4-6."""
+    dev = _require_cuda(x.device)
+    x2 = _dev_f32(x, dev).reshape(-1, x.shape[-1])
+    y = torch.empty_like(x2)
+    with torch.cuda.device(dev):
+        check(lib().mpb200_unit_norm(_ptr(x2), _ptr(y), x2.shape[0], x2.shape[1], C.c_float(eps), _stream_ptr(dev)),
+              "mpb200_unit_norm")
+    return y.view(x.shape)
+
+
+def gather_atoms(d_unit: torch.Tensor, atom: torch.Tensor, val: torch.Tensor) -> torch.Tensor:
+    """``val[e] * d_unit[atom[e]]`` as an (E, A) tensor (modules/matchingpursuit.py:305)."""
+    dev = d_unit.device
+    n = atom.numel()
+    out = torch.empty(n, d_unit.shape[1], device=dev, dtype=torch.float32)
+    if n:
+        atom = atom.to(torch.int32).contiguous()
+        val = val.to(torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            check(lib().mpb200_gather_atoms(_ptr(out), _ptr(d_unit), d_unit.shape[0], d_unit.shape[1], _ptr(atom),
+                                            _ptr(val), n, _stream_ptr(dev)), "mpb200_gather_atoms")
+    return out
+
+
+def _row_offsets(row_index: torch.Tensor, n_rows: int):
+    """Stable sort of the events by destination row -> (order, int32 offsets (n_rows+1))."""
+    order = torch.sort(row_index.to(torch.int64), stable=True)[1]
+    counts = torch.bincount(row_index.to(torch.int64), minlength=n_rows)
+    offsets = torch.zeros(n_rows + 1, device=row_index.device, dtype=torch.int32)
+    offsets[1:] = torch.cumsum(counts, 0).to(torch.int32)
+    return order, offsets
+
+
+def scatter_add(out: torch.Tensor, d_unit: torch.Tensor, atom, batch_index, pos, val) -> torch.Tensor:
+    """``out[b, p:p+A] += val * d_unit[atom]`` for every event in list order,
+    truncated at the right edge (modules/matchingpursuit.py:20-58, :48)."""
+    dev = out.device
+    b, n = out.shape[0], out.shape[-1]
+    ne = atom.numel()
+    if ne:
+        i32 = lambda t: t.reshape(-1).to(device=dev, dtype=torch.int32)
+        atom, batch_index, pos = i32(atom), i32(batch_index), i32(pos)
+        val = val.reshape(-1).to(device=dev, dtype=torch.float32)
+        order, offsets = _row_offsets(batch_index, b)
+        atom, batch_index, pos, val = (t[order].contiguous() for t in (atom, batch_index, pos, val))
+        with torch.cuda.device(dev):
+            check(lib().mpb200_scatter_add(_ptr(out), b, n, _ptr(d_unit), d_unit.shape[0], d_unit.shape[1],
+                                           _ptr(atom), _ptr(batch_index), _ptr(pos), _ptr(val), _ptr(offsets), ne,
+                                           _stream_ptr(dev)), "mpb200_scatter_add")
+    return out
+
+
+def scatter_rows(out: torch.Tensor, rows: torch.Tensor, row_index, pos) -> torch.Tensor:
+    """``out2d[row_index[e], pos[e]:pos[e]+A] += rows[e]`` in list order, truncated
+    at the right edge; ``out`` is viewed as (-1, N) (modules/matchingpursuit.py:41-52)."""
+    dev = out.device
+    n = out.shape[-1]
+    n_rows = out.numel() // n
+    ne = rows.shape[0]
+    if ne:
+        row_index = row_index.reshape(-1).to(device=dev, dtype=torch.int32)
+        pos = pos.reshape(-1).to(device=dev, dtype=torch.int32)
+        order, offsets = _row_offsets(row_index, n_rows)
+        rows = rows.to(device=dev, dtype=torch.float32)[order].contiguous()
+        row_index, pos = row_index[order].contiguous(), pos[order].contiguous()
+        with torch.cuda.device(dev):
+            check(lib().mpb200_scatter_rows(_ptr(out), n_rows, n, _ptr(rows), rows.shape[1], _ptr(row_index),
+                                            _ptr(pos), _ptr(offsets), ne, _stream_ptr(dev)), "mpb200_scatter_rows")
+    return out
+
+
+def select_dense(fm: torch.Tensor, atom_offset: int = 0, local_contrast_norm: bool = False) -> torch.Tensor:
+    """Per-signal signed argmax of a dense (B, K, N) CUDA map with the
+    reference tie-break -> (B, 4) int32 best records
+    (modules/matchingpursuit.py:298-303; with ``local_contrast_norm`` :286-296)."""
+    dev = _require_cuda(fm.device)
+    b, k, n = fm.shape
+    fm = _dev_f32(fm, dev)
+    out = torch.empty(b, 4, device=dev, dtype=torch.int32)
+    fn = lib().mpb200_select_lcn if local_contrast_norm else lib().mpb200_select_dense
+    with torch.cuda.device(dev):
+        check(fn(_ptr(fm), b, k, n, atom_offset, _ptr(out), _stream_ptr(dev)), "mpb200_select_dense")
+    return out
+
+
+def subtract(residual: torch.Tensor, d_unit: torch.Tensor, winner: torch.Tensor) -> torch.Tensor:
+    """In place: ``residual[b, p:p+A] -= value * d_unit[atom]`` for one winner per
+    signal (modules/matchingpursuit.py:326-328)."""
+    dev = residual.device
+    b, n = residual.shape[0], residual.shape[-1]
+    with torch.cuda.device(dev):
+        check(lib().mpb200_subtract(_ptr(residual), b, n, _ptr(d_unit), d_unit.shape[0], d_unit.shape[1],
+                                    _ptr(winner), _stream_ptr(dev)), "mpb200_subtract")
+    return residual

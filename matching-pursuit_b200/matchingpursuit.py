@@ -1,0 +1,394 @@
+"""Drop-in counterparts of the reference's ``modules/matchingpursuit.py``.
+
+Same names, positional/keyword signatures and return structures as the
+reference (paths below are relative to the reference tree):
+
+* :func:`sparse_code`            -- modules/matchingpursuit.py:229-345
+* :func:`sparse_feature_map`     -- modules/matchingpursuit.py:68-125
+* :func:`build_scatter_segments` -- modules/matchingpursuit.py:20-58
+* :func:`flatten_atom_dict`      -- modules/matchingpursuit.py:61-65
+* :func:`dictionary_learning_step` -- modules/matchingpursuit.py:348-419
+  (the caller; its only expensive call is ``sparse_code``)
+
+The greedy loop itself runs in the CUDA library (``include/mpb200.h``); this
+module only converts between the reference's Python data formats and the
+packed ``(atom, position, value)`` arrays the library works on.  Keyword-only
+extras (``mode``, ``plan``) select engine behaviour and do not exist in the
+reference.
+"""
+from __future__ import annotations
+
+from collections import defaultdict
+from typing import Callable, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import engine
+from ._lib import MpbError
+from .engine import Plan
+
+# --------------------------------------------------------------------------
+# plan cache: plans are expensive to size (workspaces) but cheap to re-aim at a
+# new dictionary, which the reference allows to change on every call.
+# --------------------------------------------------------------------------
+_PLAN_CACHE: "dict[tuple, Plan]" = {}
+_PLAN_CACHE_MAX = 4
+
+
+def get_plan(n_atoms: int, atom_size: int, n_samples: int, batch: int, device, mode: str = "auto") -> Plan:
+    dev = engine._require_cuda(device)
+    key = (dev.index, n_atoms, atom_size, n_samples, mode)
+    plan = _PLAN_CACHE.get(key)
+    if plan is None or plan.max_batch < batch:
+        if plan is not None:
+            plan.close()
+            del _PLAN_CACHE[key]
+        while len(_PLAN_CACHE) >= _PLAN_CACHE_MAX:
+            _PLAN_CACHE.pop(next(iter(_PLAN_CACHE))).close()
+        plan = Plan(n_atoms, atom_size, n_samples, batch, mode=mode, device=dev)
+        _PLAN_CACHE[key] = plan
+    return plan
+
+
+def clear_plan_cache() -> None:
+    while _PLAN_CACHE:
+        _PLAN_CACHE.popitem()[1].close()
+
+
+def _work_device(signal: torch.Tensor, device=None) -> torch.device:
+    """CUDA device the pursuit runs on: the signal's own, else ``device``, else the current one."""
+    if signal.is_cuda:
+        return signal.device
+    return engine._require_cuda(device if (device is not None and torch.device(device).type == "cuda") else None)
+
+
+# --------------------------------------------------------------------------
+# events
+# --------------------------------------------------------------------------
+class EventList(list):
+    """A list of reference-format event tuples ``(atom:int, batch:int,
+    pos: int64 (1,1), scaled_atom: float32 (1,1,A))`` that also carries the
+    packed arrays it was built from, so decoders can skip re-packing."""
+    packed = None  # (atom int64 (E,), batch int64 (E,), pos int64 (E,), rows float32 (E,A)) in list order
+
+
+def _events_from_packed(atom: torch.Tensor, batch_idx: torch.Tensor, pos: torch.Tensor,
+                        rows: torch.Tensor) -> EventList:
+    """Tuples in the order given.  ``atom``/``batch_idx`` int64 (E,), ``pos``
+    int64 (E,), ``rows`` (E, A) on the output device."""
+    a_host = atom.tolist()
+    b_host = batch_idx.tolist()
+    a_size = rows.shape[1]
+    pos2 = pos.view(-1, 1, 1)
+    rows3 = rows.view(-1, 1, 1, a_size)
+    out = EventList((a_host[e], b_host[e], pos2[e], rows3[e]) for e in range(len(a_host)))
+    out.packed = (atom, batch_idx, pos, rows)
+    return out
+
+
+def _first_seen_grouping(atom_step_major: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """Order of the reference's ``instances`` dict: atoms keyed in first-seen
+    order, events of one atom in step-major/batch-minor order
+    (modules/matchingpursuit.py:261, 321).  Returns (permutation of the event
+    list, atoms in first-seen order)."""
+    uniq, first = np.unique(atom_step_major, return_index=True)
+    seen_order = uniq[np.argsort(first, kind="stable")]
+    rank = np.empty(int(uniq.max()) + 1 if uniq.size else 0, dtype=np.int64)
+    rank[seen_order] = np.arange(seen_order.size)
+    perm = np.argsort(rank[atom_step_major], kind="stable")
+    return perm, seen_order
+
+
+def flatten_atom_dict(atom_dict):
+    """Concatenate the per-atom event lists (modules/matchingpursuit.py:61-65)."""
+    flat = []
+    for events in atom_dict.values():
+        flat.extend(events)
+    return flat
+
+
+# --------------------------------------------------------------------------
+# decode
+# --------------------------------------------------------------------------
+def build_scatter_segments(n_samples, atom_size, device=None):
+    """Decoder closure (modules/matchingpursuit.py:20-58).
+
+    ``scatter_segments(x, inst)``: ``x`` is a shape tuple (fresh float32 zeros)
+    or a tensor to add onto; every event ``(atom, batch, pos, scaled_atom)`` is
+    added at ``pos`` (one channel) or assigned to channel = that batch row's
+    running event count (several channels, shape-tuple form only); atoms that
+    overhang the right edge are truncated.  The reference allocates on its
+    global ``util.device``; here the buffer lives on ``device`` (default: the
+    device of the events, else the current CUDA device)."""
+
+    def scatter_segments(x, inst):
+        inst = inst if isinstance(inst, list) else list(inst)
+        packed = getattr(inst, "packed", None)
+        if packed is not None and len(inst) == packed[0].numel():
+            _, bidx, pos, rows = packed
+        elif len(inst) == 0:
+            bidx = pos = torch.zeros(0, dtype=torch.int64)
+            rows = torch.zeros(0, atom_size)
+        else:
+            bidx = torch.tensor([int(ev[1]) for ev in inst], dtype=torch.int64)
+            pos = torch.tensor([int(ev[2]) for ev in inst], dtype=torch.int64)
+            rows = torch.cat([ev[3].reshape(1, atom_size) for ev in inst], dim=0)
+        if isinstance(x, tuple):
+            dev = device
+            if dev is None:
+                dev = rows.device if rows.is_cuda else engine._require_cuda(None)
+            out_dev = torch.device(dev)
+            work = engine._require_cuda(out_dev if out_dev.type == "cuda" else None)
+            out = torch.zeros(*x, device=work, dtype=torch.float32)
+            channels = out.shape[1]
+            fresh = True
+        else:
+            out_dev = x.device
+            work = engine._require_cuda(out_dev if out_dev.type == "cuda" else None)
+            out = x.detach().to(device=work, dtype=torch.float32).clone().contiguous()
+            channels = 1
+            fresh = False
+        n_ch = out.shape[1]
+        if len(inst):
+            bidx_w = bidx.to(work)
+            if fresh and channels > 1:
+                # channel = running count of this batch row's events, in list order (:45-52)
+                b_host = bidx.cpu().numpy()
+                ch = np.zeros(len(b_host), dtype=np.int64)
+                seen: dict = {}
+                for e, j in enumerate(b_host.tolist()):
+                    ch[e] = seen.get(j, 0)
+                    seen[j] = ch[e] + 1
+                row_index = bidx_w * n_ch + torch.from_numpy(ch).to(work)
+                engine.scatter_rows(out, rows.to(work), row_index, pos.to(work))
+            elif n_ch == 1:
+                engine.scatter_rows(out, rows.to(work), bidx_w, pos.to(work))
+            else:
+                # a tensor target with several channels: the reference broadcasts the add over them (:48)
+                for c in range(n_ch):
+                    engine.scatter_rows(out, rows.to(work), bidx_w * n_ch + c, pos.to(work))
+        return out if out.device == out_dev else out.to(out_dev)
+
+    return scatter_segments
+
+
+# --------------------------------------------------------------------------
+# the pursuit
+# --------------------------------------------------------------------------
+def _needs_grad(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
+
+
+def _pursuit_dense(sig2d: torch.Tensor, plan: Plan, n_steps: int, compute_feature_map, on_map, on_select,
+                   local_contrast_norm: bool):
+    """Pursuit that materialises the dense (B,K,N) map every step -- the
+    schedule of the reference loop, needed whenever a caller-supplied callback
+    must see (or supply) that map (modules/matchingpursuit.py:272-273, 283,
+    324) or the selection is not the plain maximum (:286-296).  Correlation,
+    selection and subtraction are still library kernels."""
+    b, n = sig2d.shape
+    dev = sig2d.device
+    du = plan.unit_dictionary()
+    residual = sig2d.clone()
+    atom = torch.empty(n_steps, b, device=dev, dtype=torch.int32)
+    pos = torch.empty(n_steps, b, device=dev, dtype=torch.int32)
+    val = torch.empty(n_steps, b, device=dev, dtype=torch.float32)
+    for step in range(n_steps):
+        if compute_feature_map is not None:
+            fm = compute_feature_map(residual.view(b, 1, n), du)
+            fm = fm.to(device=dev, dtype=torch.float32).contiguous().view(b, plan.n_atoms, n)
+        else:
+            fm = plan.correlate(residual)
+        if on_map is not None:
+            on_map(step, fm, du)
+        best = engine.select_dense(fm, local_contrast_norm=local_contrast_norm)
+        v, k, p = engine.unpack_best(best)
+        atom[step], pos[step], val[step] = k, p, v
+        if on_select is not None:
+            on_select(step, fm, k, p, v, du)
+        engine.subtract(residual, du, best)
+    return atom.t().contiguous(), pos.t().contiguous(), val.t().contiguous(), residual, du
+
+
+def _run(signal: torch.Tensor, d: torch.Tensor, n_steps: int, device, approx, mode: str, plan: Optional[Plan],
+         dense_kwargs: Optional[dict] = None):
+    """Common front end: returns packed (atom, pos, val) int32/int32/float32
+    (B,S), the residual (B,N), the unit dictionary and the work device."""
+    b = signal.shape[0]
+    n = signal.shape[-1]
+    k, a = d.shape[0], d.shape[-1]
+    work = plan.device if plan is not None else _work_device(signal, device)
+    sig2d = engine._dev_f32(signal, work, (b, n))
+    if plan is None:
+        plan = get_plan(k, a, n, b, work, mode)
+        plan.set_dictionary(d)
+    if isinstance(approx, slice) or (isinstance(approx, int) and not isinstance(approx, bool) and approx < n):
+        raise NotImplementedError(
+            "approx=slice / approx=int<N (band-limited or top-k-bin correlation, modules/conv.py:24-47) "
+            "is not part of the engine yet; pass approx=None or approx>=n_samples")
+    if dense_kwargs is not None:
+        atom, pos, val, residual, du = _pursuit_dense(sig2d, plan, n_steps, **dense_kwargs)
+    else:
+        atom, pos, val, residual = plan.sparse_code(sig2d, n_steps, want_residual=True)
+        du = None
+    return plan, atom, pos, val, residual, du, work
+
+
+def sparse_code(signal, d, n_steps=100, device=None, approx=None, flatten=False, extract_atom_embedding=None,
+                visit_key_point=None, return_residual=False, local_contrast_norm=False,
+                return_sparse_feature_map=False, compute_feature_map=None, fft_convolution=False, *,
+                mode: str = "auto", plan: Optional[Plan] = None):
+    """Greedy convolutional matching pursuit (modules/matchingpursuit.py:229-345).
+
+    ``signal`` (B,1,N), ``d`` (K,A) or (K,1,A); neither is modified; the
+    dictionary is unit-normed first (:254).  Exactly ``n_steps`` events per
+    signal.  Return conventions follow the reference (:332-345).  ``device``
+    and ``fft_convolution`` are accepted and ignored, as there.  Tensors in the
+    results live on ``signal.device``."""
+    batch, channels, time = signal.shape
+    if channels != 1:
+        raise NotImplementedError("multi-channel signals fail in the reference's scatter_segments "
+                                  "(modules/matchingpursuit.py:50); only (B,1,N) is supported")
+    if _needs_grad(signal, d):
+        raise MpbError("inputs require grad: the CUDA pursuit is forward-only; run under torch.no_grad() "
+                       "or use matching_pursuit_b200.autograd for the differentiable re-evaluation")
+    n_samples = time
+    n_atoms, atom_size = d.shape[0], d.shape[-1]
+    out_dev = signal.device
+    embeddings = []
+
+    dense = None
+    if (compute_feature_map is not None or extract_atom_embedding is not None or visit_key_point is not None
+            or local_contrast_norm):
+        def on_map(step, fm, du):
+            embeddings.append(extract_atom_embedding(fm, du))                # :282-283
+
+        def on_select(step, fm, k, p, v, du):
+            scaled = engine.gather_atoms(du, k, v)
+            k_host = k.tolist()
+            for j in range(batch):
+                visit_key_point(fm[j].view(n_atoms, n_samples), k_host[j], p[j].view(1).to(torch.int64),
+                                scaled[j].view(atom_size))
+
+        dense = dict(compute_feature_map=compute_feature_map,
+                     on_map=on_map if extract_atom_embedding is not None else None,
+                     on_select=on_select if visit_key_point is not None else None,
+                     local_contrast_norm=bool(local_contrast_norm))
+
+    plan_, atom, pos, val, residual, du, work = _run(signal, d, n_steps, device, approx, mode, plan, dense)
+    residual = residual.view(batch, 1, n_samples).to(out_dev)
+
+    if extract_atom_embedding is not None:                                   # :332-333
+        return embeddings, residual
+
+    scatter_segments = build_scatter_segments(n_samples, atom_size, device=out_dev)
+
+    # events in the reference's order of creation: step-major, batch-minor
+    if du is None:
+        du = plan_.unit_dictionary()
+    atom_sm = atom.t().reshape(-1)
+    val_sm = val.t().reshape(-1)
+    pos_sm = pos.t().reshape(-1)
+    rows = engine.gather_atoms(du, atom_sm, val_sm)                          # :305
+    batch_sm = torch.arange(batch, device=work, dtype=torch.int64).repeat(n_steps)
+    atom_host = atom_sm.cpu().numpy().astype(np.int64)
+    perm, seen_order = _first_seen_grouping(atom_host) if atom_host.size else (np.zeros(0, np.int64), atom_host)
+    perm_t = torch.from_numpy(perm).to(work)
+    g_atom = atom_sm.to(torch.int64)[perm_t].to(out_dev)
+    g_batch = batch_sm[perm_t].to(out_dev)
+    g_pos = pos_sm.to(torch.int64)[perm_t].to(out_dev)
+    g_rows = rows[perm_t].to(out_dev)
+    flattened = _events_from_packed(g_atom, g_batch, g_pos, g_rows)
+
+    if not flatten:                                                          # :335-336
+        instances = defaultdict(list)
+        counts = np.bincount(atom_host, minlength=n_atoms) if atom_host.size else np.zeros(n_atoms, np.int64)
+        start = 0
+        for ai in seen_order.tolist():
+            c = int(counts[ai])
+            group = EventList(flattened[start:start + c])
+            group.packed = (g_atom[start:start + c], g_batch[start:start + c], g_pos[start:start + c],
+                            g_rows[start:start + c])
+            instances[ai] = group
+            start += c
+        return instances, scatter_segments
+    if return_residual:                                                      # :337-339
+        return flattened, scatter_segments, residual
+    if return_sparse_feature_map:                                            # :340-342, :317-318
+        sfm = torch.zeros(batch, n_atoms, n_samples, device=work)
+        sfm.index_put_((batch_sm, atom_sm.to(torch.int64), pos_sm.to(torch.int64)), val_sm, accumulate=True)
+        return flattened, scatter_segments, sfm.to(out_dev)
+    return flattened, scatter_segments                                       # :343-345
+
+
+def sparse_code_arrays(signal, d, n_steps=100, *, mode: str = "auto", plan: Optional[Plan] = None, device=None):
+    """Array-level form of :func:`sparse_code` for large batches: returns
+    ``(atom int32 (B,S), pos int32 (B,S), val float32 (B,S), residual (B,1,N))``
+    on ``signal.device`` without building B*S Python tuples."""
+    batch = signal.shape[0]
+    n_samples = signal.shape[-1]
+    if _needs_grad(signal, d):
+        raise MpbError("inputs require grad: the CUDA pursuit is forward-only")
+    out_dev = signal.device
+    _, atom, pos, val, residual, _, _ = _run(signal, d, n_steps, device, None, mode, plan)
+    return atom.to(out_dev), pos.to(out_dev), val.to(out_dev), residual.view(batch, 1, n_samples).to(out_dev)
+
+
+def sparse_feature_map(signal, d, n_steps=100, device=None, approx=None, pooling=None, return_residual=False, *,
+                       mode: str = "auto", plan: Optional[Plan] = None):
+    """Dense (B,K,N) accumulation of the winners (modules/matchingpursuit.py:68-125):
+    each step adds the winning value at its (atom, position) -- the forward
+    value of ``soft_dirac(f) * f`` (:100-101).  ``pooling`` is accepted and
+    ignored as in the reference; ``device`` places the dense map (:84-85)."""
+    if _needs_grad(signal, d):
+        raise MpbError("inputs require grad: the CUDA pursuit is forward-only")
+    b = signal.shape[0]
+    sig = signal.reshape(b, 1, -1)
+    n = sig.shape[-1]
+    k = d.shape[0]
+    _, atom, pos, val, residual, _, work = _run(sig, d, n_steps, device if device is not None else None, approx,
+                                                mode, plan)
+    fm = torch.zeros(b, k, n, device=work)
+    rows = torch.arange(b, device=work, dtype=torch.int64).repeat_interleave(n_steps)
+    fm.index_put_((rows, atom.reshape(-1).to(torch.int64), pos.reshape(-1).to(torch.int64)), val.reshape(-1),
+                  accumulate=True)
+    fm_dev = torch.device(device) if device is not None else signal.device
+    fm = fm.to(fm_dev)
+    if return_residual:
+        return fm, residual.view(b, 1, n).to(signal.device)
+    return fm
+
+
+def dictionary_learning_step(signal, d, n_steps: int = 100, device=None, approx=None,
+                             local_constrast_norm: bool = False, compute_feature_map=None, fft_convolution=False, *,
+                             mode: str = "auto"):
+    """One dictionary update (modules/matchingpursuit.py:348-419).  The coding
+    pass is the CUDA pursuit; the atom update stays in PyTorch: for every used
+    atom, in first-seen order, its instances are added back to a running copy
+    of the SIGNAL (:367), the atom becomes the unit-normed sum of the segments
+    under them (:400-406) and the re-scaled new atom is subtracted (:408-415)."""
+    batch, channels, n_samples = signal.shape
+    atom_size = d.shape[-1]
+    work = _work_device(signal, device)
+    with torch.no_grad():
+        d_new = engine.unit_norm(engine._dev_f32(d, work).reshape(d.shape[0], -1)).view(d.shape).clone()
+        running = engine._dev_f32(signal, work).clone()
+        instances, _ = sparse_code(signal, d, n_steps=n_steps, device=device, approx=approx,
+                                   local_contrast_norm=local_constrast_norm,
+                                   compute_feature_map=compute_feature_map, fft_convolution=fft_convolution, mode=mode)
+        flat_rows = running.view(batch * channels, n_samples)
+        for index, inst in instances.items():
+            _, bidx, pos, rows = inst.packed
+            bidx, pos, rows = bidx.to(work), pos.to(work), rows.to(work)
+            engine.scatter_rows(flat_rows, rows, bidx, pos)                   # add the instances back (:395-396)
+            padded = torch.nn.functional.pad(running.view(batch, n_samples), (0, atom_size))
+            gather_idx = pos.view(-1, 1) + torch.arange(atom_size, device=work).view(1, -1)
+            segments = padded[bidx.view(-1, 1), gather_idx]                   # (E, A)  (:369-378)
+            summed = torch.sum(segments, dim=0)                               # :398
+            new_atom = summed / (torch.norm(summed) + 1e-8)                   # unit_norm (:403-404)
+            d_new.view(d.shape[0], -1)[index] = new_atom
+            amps = torch.norm(rows, dim=-1, keepdim=True)                     # :409-411
+            engine.scatter_rows(flat_rows, -(new_atom.view(1, -1) * amps), bidx, pos)
+        out = engine.unit_norm(d_new.reshape(d.shape[0], -1)).view(d.shape)   # :417
+    return out.to(d.device)

@@ -1,0 +1,336 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes binding ->
+``libmpb200.so``), against the CPU oracle and the committed golden vectors that
+the unmodified reference produced (tests/golden, oracle/make_golden.py).
+
+Tolerances (BASELINE.json north_star): identical (atom, position) wherever the
+top-2 relative margin exceeds 1e-5; amplitudes and residual energy within 1e-4
+relative."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import matching_pursuit_b200 as mpb
+from oracle import mp_oracle as O
+from parity import MARGIN, RTOL, compare_trace, compare_with_oracle_trace
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SC_CASES = sorted(p for p in glob.glob(os.path.join(GOLDEN, "sc_*.npz")))
+DEV = "cuda:0"
+
+
+def run_plan(signal, d, steps, mode="recorrelate", atom_range=None):
+    b, _, n = signal.shape
+    plan = mpb.Plan(d.shape[0], d.shape[1], n, b, mode=mode, device=DEV, atom_range=atom_range)
+    plan.set_dictionary(d)
+    atom, pos, val, res = plan.sparse_code(signal.to(DEV), steps)
+    torch.cuda.synchronize()
+    return atom.cpu().numpy(), pos.cpu().numpy(), val.cpu().numpy(), res.cpu().numpy()
+
+
+# --------------------------------------------------------------------------
+# golden vectors from the live reference
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["recorrelate", "full"])
+@pytest.mark.parametrize("path", [p for p in SC_CASES if "lcn" not in p],
+                         ids=[os.path.basename(p)[:-4] for p in SC_CASES if "lcn" not in p])
+def test_golden_sparse_code(path, mode):
+    g = np.load(path)
+    sig, d = torch.from_numpy(g["signal"]), torch.from_numpy(g["d"])
+    atom, pos, val, res = run_plan(sig, d, int(g["steps"]), mode)
+    compare_trace(g["atom"], g["pos"], g["absval"], g["margin"], g["residual"][:, 0], atom.T, pos.T, val.T, res)
+
+
+def test_golden_zero_signal_is_exact():
+    g = np.load(os.path.join(GOLDEN, "sc_zero_b1_n128_k4_a16.npz"))
+    atom, pos, val, res = run_plan(torch.from_numpy(g["signal"]), torch.from_numpy(g["d"]), 3)
+    assert (atom == 0).all() and (pos == 0).all() and (val == 0).all() and (res == 0).all()
+
+
+def test_golden_local_contrast_norm():
+    g = np.load(os.path.join(GOLDEN, "sc_lcn_b2_n512_k12_a32.npz"))
+    sig, d = torch.from_numpy(g["signal"]), torch.from_numpy(g["d"])
+    flat, scatter, residual = mpb.sparse_code(sig.to(DEV), d.to(DEV), int(g["steps"]), flatten=True,
+                                              return_residual=True, local_contrast_norm=True)
+    if (g["margin"] > MARGIN).all():
+        order = np.array([(ai, j, int(p)) for ai, j, p, a in flat], dtype=np.int64)
+        assert np.array_equal(order, g["flat_order"])
+        np.testing.assert_allclose(residual.cpu().numpy(), g["residual"], rtol=1e-4, atol=2e-5)
+
+
+def test_golden_dense_correlation():
+    g = np.load(os.path.join(GOLDEN, "corr_helpers.npz"))
+    sig, d = torch.from_numpy(g["signal"]), torch.from_numpy(g["d"])
+    plan = mpb.Plan(d.shape[0], d.shape[1], sig.shape[-1], sig.shape[0], device=DEV, mode="recorrelate")
+    plan.set_dictionary(d)
+    fm = plan.correlate(sig.to(DEV).view(sig.shape[0], -1)).cpu().numpy()
+    # the golden map was computed with the dictionary as given (already unit norm here)
+    np.testing.assert_allclose(fm, g["torch_conv"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(plan.unit_dictionary().cpu().numpy(), O.unit_norm(d).numpy(), rtol=0, atol=1e-7)
+
+
+def test_golden_sparse_feature_map():
+    g = np.load(os.path.join(GOLDEN, "feature_map.npz"))
+    sig, d = torch.from_numpy(g["signal"]), torch.from_numpy(g["d"])
+    fm, res = mpb.sparse_feature_map(sig.to(DEV), d.to(DEV), n_steps=9, return_residual=True)
+    fm, res = fm.cpu().numpy(), res.cpu().numpy()
+    assert np.array_equal(fm != 0, g["fm"] != 0)
+    np.testing.assert_allclose(fm, g["fm"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(res, g["residual"], rtol=1e-4, atol=2e-6)
+
+
+def test_golden_dictionary_learning_step():
+    g = np.load(os.path.join(GOLDEN, "dictionary_learning.npz"))
+    sig, d = torch.from_numpy(g["signal"]), torch.from_numpy(g["d"])
+    learned = mpb.dictionary_learning_step(sig.to(DEV), d.to(DEV).clone(), n_steps=8)
+    np.testing.assert_allclose(learned.cpu().numpy(), g["learned"], rtol=1e-4, atol=1e-5)
+
+
+# --------------------------------------------------------------------------
+# oracle on seeded inputs (sizes the oracle finishes in seconds)
+# --------------------------------------------------------------------------
+CASES = [
+    # (K, A, N, B, S, family)
+    (32, 64, 2048, 4, 40, "planted"),
+    (33, 100, 3000, 3, 30, "noise"),        # odd atom count, ragged sizes
+    (64, 256, 8192, 2, 48, "planted"),
+    (16, 512, 4096, 2, 24, "noise"),        # M = 2048
+    (8, 1024, 8192, 2, 16, "planted"),      # M = 4096
+    (6, 2048, 16384, 1, 12, "planted"),     # M = 8192
+    (5, 700, 700, 2, 8, "noise"),           # atom as long as the signal
+]
+
+
+def make_case(k, a, n, b, s, family):
+    d = O.make_dictionary(k, a, seed=k + a)
+    if family == "planted":
+        sig = O.make_planted_signals(d, b, n, max(4, s // 2), seed=n)
+    else:
+        sig = O.make_noise_signals(b, n, seed=n)
+    return sig, d
+
+
+@pytest.mark.parametrize("mode", ["recorrelate", "full"])
+@pytest.mark.parametrize("case", CASES, ids=[f"K{c[0]}_A{c[1]}_N{c[2]}_B{c[3]}_{c[5]}" for c in CASES])
+def test_oracle_parity(case, mode):
+    k, a, n, b, s, family = case
+    sig, d = make_case(*case)
+    tr = O.greedy_pursuit(sig, d, s, want_margin=True)
+    atom, pos, val, res = run_plan(sig, d, s, mode)
+    checked = compare_with_oracle_trace(tr, atom, pos, val, res)
+    assert checked > 0
+
+
+def test_config1_full_size():
+    """BASELINE.json configs[0]: 1 x 2^15 samples, 512 atoms x 512, 32 iterations."""
+    d = O.make_dictionary(512, 512, seed=0)
+    sig = O.make_planted_signals(d, 1, 2 ** 15, 32, seed=1)
+    tr = O.greedy_pursuit(sig, d, 32, want_margin=True)
+    atom, pos, val, res = run_plan(sig, d, 32)
+    assert compare_with_oracle_trace(tr, atom, pos, val, res) >= 16
+
+
+def test_host_entry_equals_device_entry():
+    sig, d = make_case(32, 64, 2048, 4, 40, "planted")
+    plan = mpb.Plan(32, 64, 2048, 4, device=DEV, mode="recorrelate").set_dictionary(d)
+    a0, p0, v0, r0 = plan.sparse_code(sig.to(DEV), 20)
+    a1, p1, v1, r1 = plan.sparse_code_host(sig.view(4, -1), 20)
+    assert torch.equal(a0.cpu(), a1) and torch.equal(p0.cpu(), p1) and torch.equal(v0.cpu(), v1)
+    assert torch.equal(r0.cpu(), r1)
+    # inputs are not modified, repeated calls are reproducible
+    a2, p2, v2, r2 = plan.sparse_code(sig.to(DEV), 20)
+    assert torch.equal(a0, a2) and torch.equal(v0, v2) and torch.equal(r0, r2)
+
+
+def test_atom_sharded_stepwise_equals_oracle():
+    """Atom sharding emulated on one GPU: R plans own disjoint atom ranges, their
+    local winners are reduced with the reference tie-break, every plan applies
+    the global winner."""
+    k, a, n, b, s = 37, 128, 4096, 3, 24
+    d = O.make_dictionary(k, a, seed=5)
+    sig = O.make_planted_signals(d, b, n, 12, seed=6)
+    tr = O.greedy_pursuit(sig, d, s, want_margin=True)
+    bounds = [0, 11, 24, 37]
+    plans = [mpb.Plan(k, a, n, b, device=DEV, mode="recorrelate", atom_range=(lo, hi)).set_dictionary(d)
+             for lo, hi in zip(bounds[:-1], bounds[1:])]
+    for p in plans:
+        p.begin(sig.to(DEV))
+    atoms, poss, vals = [], [], []
+    for _ in range(s):
+        cand = torch.cat([p.local_best() for p in plans], dim=0)
+        win = mpb.reduce_best(cand, len(plans), b)
+        v, kk, pp = mpb.unpack_best(win)
+        atoms.append(kk.cpu().numpy()); poss.append(pp.cpu().numpy()); vals.append(v.cpu().numpy())
+        for p in plans:
+            p.apply(win)
+    res = plans[0].residual().cpu().numpy()
+    for p in plans[1:]:
+        assert np.array_equal(p.residual().cpu().numpy(), res)
+    compare_trace(tr.atom.numpy(), tr.pos.numpy(), tr.val.abs().numpy(), tr.margin.numpy(), tr.residual.numpy()[:, 0],
+                  np.stack(atoms), np.stack(poss), np.stack(vals), res)
+
+
+# --------------------------------------------------------------------------
+# drop-in return conventions
+# --------------------------------------------------------------------------
+def test_dropin_return_conventions():
+    sig, d = make_case(32, 64, 2048, 4, 40, "planted")
+    s = 24
+    tr = O.greedy_pursuit(sig, d, s, want_margin=True)
+    if not (tr.margin.numpy() > MARGIN).all():
+        pytest.skip("ambiguous step in the seeded case")
+    want_flat, want_scatter, want_res = O.sparse_code(sig, d, s, flatten=True, return_residual=True)
+    flat, scatter, res = mpb.sparse_code(sig.to(DEV), d.to(DEV), s, flatten=True, return_residual=True)
+    assert [(ai, j, int(p)) for ai, j, p, _ in flat] == [(ai, j, int(p)) for ai, j, p, _ in want_flat]
+    ai, j, p, a = flat[0]
+    assert isinstance(ai, int) and isinstance(j, int) and p.shape == (1, 1) and p.dtype == torch.int64
+    assert a.shape == (1, 1, 64) and a.dtype == torch.float32 and a.is_cuda
+    for (_, _, _, a0), (_, _, _, a1) in zip(flat, want_flat):
+        np.testing.assert_allclose(a0.cpu().numpy(), a1.numpy(), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(res.cpu().numpy(), want_res.numpy(), rtol=1e-4, atol=2e-6)
+    recon = scatter(tuple(sig.shape), flat)
+    np.testing.assert_allclose(recon.cpu().numpy(), want_scatter(tuple(sig.shape), want_flat).numpy(),
+                               rtol=1e-4, atol=2e-6)
+    # signal = decode + residual
+    np.testing.assert_allclose((recon + res).cpu().numpy(), sig.numpy(), atol=5e-6)
+    # grouped form: keys in first-seen order
+    inst, _ = mpb.sparse_code(sig.to(DEV), d.to(DEV), s)
+    want_inst, _ = O.sparse_code(sig, d, s)
+    assert list(inst.keys()) == list(want_inst.keys())
+    for key in inst:
+        assert [(x[1], int(x[2])) for x in inst[key]] == [(x[1], int(x[2])) for x in want_inst[key]]
+    # sparse feature map form
+    _, _, sfm = mpb.sparse_code(sig.to(DEV), d.to(DEV), s, flatten=True, return_sparse_feature_map=True)
+    _, _, want_sfm = O.sparse_code(sig, d, s, flatten=True, return_sparse_feature_map=True)
+    np.testing.assert_allclose(sfm.cpu().numpy(), want_sfm.numpy(), rtol=1e-4, atol=1e-6)
+    # CPU tensors in -> CPU tensors out
+    flat_c, _, res_c = mpb.sparse_code(sig, d, s, flatten=True, return_residual=True)
+    assert not res_c.is_cuda and not flat_c[0][3].is_cuda
+    assert [(ai, j, int(p)) for ai, j, p, _ in flat_c] == [(ai, j, int(p)) for ai, j, p, _ in want_flat]
+
+
+def test_dropin_callbacks_see_the_dense_map():
+    sig, d = make_case(16, 32, 512, 2, 10, "planted")
+    s = 6
+    seen, want_seen = [], []
+
+    def visit(fm, ai, p, a):
+        seen.append((ai, int(p), tuple(fm.shape), float(a.abs().max())))
+
+    def want_visit(fm, ai, p, a):
+        want_seen.append((ai, int(p), tuple(fm.shape), float(a.abs().max())))
+
+    mpb.sparse_code(sig.to(DEV), d.to(DEV), s, visit_key_point=visit)
+    O.sparse_code(sig, d, s, visit_key_point=want_visit)
+    assert [x[:3] for x in seen] == [x[:3] for x in want_seen]
+    np.testing.assert_allclose([x[3] for x in seen], [x[3] for x in want_seen], rtol=1e-4)
+    # compute_feature_map seam: a callback that supplies the map (here: the library's own dense correlation)
+    calls = []
+
+    def cfm(residual, du):
+        calls.append(tuple(residual.shape))
+        plan = mpb.get_plan(du.shape[0], du.shape[1], residual.shape[-1], residual.shape[0], residual.device)
+        return plan.correlate(residual.view(residual.shape[0], -1))
+
+    flat, _ = mpb.sparse_code(sig.to(DEV), d.to(DEV), s, flatten=True, compute_feature_map=cfm)
+    want_flat, _ = O.sparse_code(sig, d, s, flatten=True)
+    assert calls == [(2, 1, 512)] * s
+    assert [(ai, j, int(p)) for ai, j, p, _ in flat] == [(ai, j, int(p)) for ai, j, p, _ in want_flat]
+    emb, res = mpb.sparse_code(sig.to(DEV), d.to(DEV), s, extract_atom_embedding=lambda fm, dd: fm.amax(dim=(1, 2)))
+    want_emb, want_res = O.sparse_code(sig, d, s, extract_atom_embedding=lambda fm, dd: fm.amax(dim=(1, 2)))
+    np.testing.assert_allclose(torch.stack(emb).cpu().numpy(), torch.stack(want_emb).numpy(), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(res.cpu().numpy(), want_res.numpy(), rtol=1e-4, atol=2e-6)
+
+
+def test_select_dense_tie_break_and_subtract():
+    fm = torch.zeros(2, 3, 40, device=DEV)
+    fm[0, 2, 7] = 5.0; fm[0, 1, 30] = 5.0; fm[0, 1, 31] = 5.0     # tie -> lowest atom, then lowest position
+    fm[1] = -1.0; fm[1, 0, 0] = -3.0                               # all negative: signed max, first index among ties
+    best = mpb.select_dense(fm)
+    v, k, p = mpb.unpack_best(best)
+    assert k.tolist() == [1, 0] and p.tolist() == [30, 1] and v.tolist() == [5.0, -1.0]
+    d = O.make_dictionary(3, 8, seed=1).to(DEV)
+    r = torch.ones(2, 40, device=DEV)
+    want = r.clone()
+    want[0, 30:38] -= 5.0 * d[1]
+    want[1, 1:9] -= -1.0 * d[0]
+    mpb.subtract(r, d, best)
+    assert torch.equal(r, want)
+    # right-edge truncation
+    fm2 = torch.zeros(1, 3, 40, device=DEV); fm2[0, 2, 36] = 2.0
+    best2 = mpb.select_dense(fm2)
+    r2 = torch.zeros(1, 40, device=DEV)
+    mpb.subtract(r2, d, best2)
+    assert torch.equal(r2[0, 36:], -(2.0 * d[2, :4])) and (r2[0, :36] == 0).all()
+
+
+def test_scatter_segments_modes():
+    a = 16
+    d = O.make_dictionary(4, a, seed=2)
+    events = [(1, 0, torch.tensor([[5]]), (0.5 * d[1]).view(1, 1, a)),
+              (3, 1, torch.tensor([[60]]), (2.0 * d[3]).view(1, 1, a)),     # overhangs the right edge of N=64
+              (0, 0, torch.tensor([[10]]), (-1.0 * d[0]).view(1, 1, a))]
+    want_scatter = O.make_scatter(64, a)
+    scatter = mpb.build_scatter_segments(64, a, device=DEV)
+    got = scatter((2, 1, 64), events)
+    np.testing.assert_allclose(got.cpu().numpy(), want_scatter((2, 1, 64), events).numpy(), atol=1e-7)
+    base = torch.randn(2, 1, 64)
+    got = scatter(base.to(DEV), events)
+    np.testing.assert_allclose(got.cpu().numpy(), want_scatter(base, events).numpy(), atol=1e-7)
+    # one channel per event (modules/matchingpursuit.py:50)
+    got = scatter((2, 3, 64), events)
+    np.testing.assert_allclose(got.cpu().numpy(), want_scatter((2, 3, 64), events).numpy(), atol=1e-7)
+    assert scatter((2, 1, 64), []).abs().sum().item() == 0
+
+
+# --------------------------------------------------------------------------
+# size-independent properties at sizes the oracle cannot reach
+# --------------------------------------------------------------------------
+def test_properties_at_scale():
+    """512 atoms x 1024 samples, 16 x 2^15 signals, 128 steps: the events must
+    explain the residual (signal = decode(events) + residual), every value must
+    be the correlation of the atom with the residual it was picked from, and the
+    residual energy must fall by value^2 each step (unit atoms, no truncation)."""
+    k, a, n, b, s = 512, 1024, 2 ** 15, 16, 128
+    d = O.make_dictionary(k, a, seed=0)
+    sig = O.make_planted_signals(d, b, n, 64, seed=1)
+    plan = mpb.Plan(k, a, n, b, device=DEV, mode="recorrelate").set_dictionary(d)
+    atom, pos, val, res = plan.sparse_code(sig.to(DEV), s)
+    du = plan.unit_dictionary()
+    out = torch.zeros(b, n, device=DEV)
+    rows = torch.arange(b, device=DEV).repeat_interleave(s)
+    mpb.scatter_add(out, du, atom.reshape(-1), rows, pos.reshape(-1), val.reshape(-1))
+    np.testing.assert_allclose((out + res).cpu().numpy(), sig.view(b, n).numpy(), atol=2e-5)
+    # energy bookkeeping in float64 on the host
+    e0 = (sig.view(b, n).double() ** 2).sum(-1)
+    e1 = (res.cpu().double() ** 2).sum(-1)
+    interior = (pos.cpu() + a <= n)
+    drop = (val.cpu().double() ** 2 * interior).sum(-1)
+    assert ((e0 - e1) >= 0.999 * drop - 1e-6).all()
+    assert (val.cpu()[:, 0] > 0).all() and (val.cpu() >= -1e-6).all()
+    # first step of every signal equals the oracle's (one dense correlation on the CPU is affordable)
+    fm = O.correlate_direct(sig, O.unit_norm(d))
+    v0, i0 = fm.reshape(b, -1).max(-1)
+    assert torch.equal(i0 // n, atom[:, 0].cpu().long()) and torch.equal(i0 % n, pos[:, 0].cpu().long())
+    np.testing.assert_allclose(val[:, 0].cpu().numpy(), v0.numpy(), rtol=1e-4)
+
+
+def test_errors():
+    with pytest.raises(mpb.MpbError):
+        mpb.Plan(4, 5000, 128, 1, device=DEV)            # window FFT longer than supported
+    with pytest.raises(mpb.MpbError):
+        mpb.Plan(4, 16, 128, 1, device=DEV, atom_range=(3, 2))
+    plan = mpb.Plan(4, 16, 128, 2, device=DEV)
+    with pytest.raises(mpb.MpbError):
+        plan.sparse_code(torch.zeros(1, 128, device=DEV), 2)     # dictionary not set
+    plan.set_dictionary(torch.randn(4, 16))
+    with pytest.raises(mpb.MpbError):
+        plan.sparse_code(torch.zeros(3, 128, device=DEV), 2)     # batch > max_batch
+    with pytest.raises(mpb.MpbError):
+        plan.set_dictionary(torch.randn(5, 16))
+    with pytest.raises(ValueError):
+        mpb.sparse_code(torch.zeros(128, device=DEV), torch.randn(4, 16))   # not (B,C,N), as the reference
