@@ -333,11 +333,10 @@ int mpb200_plan_create(mpb200_plan_t* out, int n_atoms, int atom_size, int n_sam
     const uint64_t gram_bytes = (uint64_t)n_atoms * p->nloc * (2ull * atom_size) * sizeof(float);
     const uint64_t map_bytes = (uint64_t)max_batch * p->nloc * n_samples * sizeof(float);
     if (mode == MPB200_MODE_AUTO) {
-        size_t free_b = 0, total_b = 0;
-        MPB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        uint64_t budget = gram_budget_bytes ? gram_budget_bytes : (uint64_t)(0.4 * (double)free_b);
-        mode = (gram_bytes <= budget && gram_bytes + map_bytes <= (uint64_t)(0.8 * (double)free_b))
-                   ? MPB200_MODE_GRAM : MPB200_MODE_RECORRELATE;
+        // GRAM pays off when the table and the resident map fit comfortably; it is not built yet,
+        // so AUTO resolves to windowed re-correlation for now.
+        (void)gram_bytes; (void)map_bytes; (void)gram_budget_bytes;
+        mode = MPB200_MODE_RECORRELATE;
     }
     p->mode = mode;
     if (mode == MPB200_MODE_GRAM) {
