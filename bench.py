@@ -38,6 +38,10 @@ WORKLOADS = {
            "BASELINE configs[1]: batch 64 x 2^15 samples, 512-atom x 1024 dictionary, 256 iterations"),
     "c1": (1, 2 ** 15, 512, 512, 32,
            "BASELINE configs[0]: 1 x 2^15 samples, 512 atoms x 512 samples, 32 iterations"),
+    # atom-sharded (not batch-sharded): handled by run_atom_sharded()
+    "c5": (1, 2 ** 20, 16384, 2048, 2048,
+           "BASELINE configs[4]: single 2^20-sample signal, 16384-atom x 2048 dictionary, 2048 iterations, "
+           "atom-sharded with a per-step NCCL all-gather of 16-byte records"),
 }
 METRIC = "MP atoms/sec (4096x2048 dict, 2^15 sig)"
 UNIT = "atoms/s"
@@ -201,12 +205,89 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------
+# atom-sharded workload (configs[4])
+# --------------------------------------------------------------------------
+def run_atom_sharded(args):
+    import torch
+    import torch.distributed as dist
+    import matching_pursuit_b200 as mpb
+    from matching_pursuit_b200.distributed import AtomShardedPursuit
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    batch, n, k, a, s, desc = WORKLOADS["c5"]
+    if args.iterations:
+        s = args.iterations
+    d, sig = make_inputs(torch, mpb, dev, batch, n, k, a, n_events=min(s, 1024), seed=1)   # same on every rank
+    pursuit = AtomShardedPursuit(k, a, n, batch, device=dev).set_dictionary(d)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        pursuit.run(sig, min(s, 64))
+    barrier()
+    launches0 = mpb.lib().mpb200_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        atom, pos, val, res = pursuit.run(sig, s)
+    e1.record()
+    barrier()
+    launches = mpb.lib().mpb200_launch_count() - launches0
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    # separate, un-timed pass with events around every exchange: per-step collective latency
+    pursuit.run(sig, min(s, 512), time_exchange=True)
+    ex = sorted(pursuit.exchange_ms)
+    # all ranks must agree on the sequence
+    if world > 1:
+        chk = torch.stack([atom.double().sum(), pos.double().sum(), val.double().sum()])
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        agree = bool(torch.equal(lo, hi))
+    else:
+        agree = True
+    if rank == 0:
+        print(json.dumps({
+            "metric": "MP atoms/sec (16384x2048 dict, 2^20 sig, atom-sharded)", "value": s * args.steps / (ms_total / 1e3),
+            "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic (planted atoms + noise, seeded)",
+            "config": {"workload": desc, "iterations": s, "atoms_per_rank": (k + world - 1) // world,
+                       "parallelism": f"atom-sharded x{world}"},
+            "gpu_launches": int(launches), "ranks_agree": agree,
+            "exchange_latency_ms": {"mean": sum(ex) / max(len(ex), 1), "p50": ex[len(ex) // 2] if ex else None,
+                                    "p99": ex[min(len(ex) - 1, int(0.99 * len(ex)))] if ex else None,
+                                    "what": "CUDA-event time around the per-step all_gather_into_tensor of "
+                                            "one 16-byte record per rank (0 at 1 GPU: no collective)"},
+            "us_per_iteration": 1e3 * ms_total / args.steps / s,
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.workload == "c5":
+        run_atom_sharded(args)
         return
     import torch
     import torch.distributed as dist
