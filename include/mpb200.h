@@ -93,6 +93,10 @@ int mpb200_plan_timing_read(mpb200_plan_t plan, double* ms_by_tag, int64_t* coun
  * atom-pair spectra (and the Gram table in GRAM mode).  The caller's buffer is
  * not modified and may be freed once `stream` has passed this call. */
 int mpb200_plan_set_dictionary(mpb200_plan_t plan, const float* d, void* stream);
+/* Same without the normalisation: the atoms are used as given -- what the
+ * correlation helpers modules/conv.py:4-9 (torch_conv) and :11-53 (fft_convolve)
+ * do, and mp.py's un-normalised atoms (mp.py:43-48). */
+int mpb200_plan_set_dictionary_raw(mpb200_plan_t plan, const float* d, void* stream);
 /* Copy of the normalised dictionary (n_atoms, atom_size). */
 int mpb200_plan_get_unit_dictionary(mpb200_plan_t plan, float* out, void* stream);
 
@@ -186,13 +190,29 @@ int mpb200_gather_atoms(float* scaled, const float* d_unit, int n_atoms, int ato
 /* y = x / (||x||_2 + eps) per row -- modules/normalization.py:4-6. */
 int mpb200_unit_norm(const float* x, float* y, int rows, int cols, float eps, void* stream);
 
-/* out[r, :n] = first n samples of the linear convolution (conjugate_b = 0) or
- * correlation (conjugate_b = 1) of a[r % rows_a, :n] with b[r % rows_b, :n],
- * both zero-padded to 2n -- replaces modules/fft.py:23-35 and
- * modules/transfer.py:548-569 for two operands (rows = max(rows_a, rows_b);
- * broadcasting over leading dimensions is done by the caller's row indexing). */
-int mpb200_fft_convolve(const float* a, int rows_a, const float* b, int rows_b, int n, int conjugate_b,
-                        float* out, void* stream);
+/* N-ary zero-padded FFT convolution -- replaces modules/fft.py:23-35 (and the
+ * identical arithmetic of modules/transfer.py:548-569): every operand row of n
+ * samples is padded to 2n, the spectra are multiplied, the product is inverted
+ * at length 2n and cropped to n.
+ *   operands      HOST array of n_ops (<= 4) DEVICE pointers, operand i is (operand_rows[i], n)
+ *   row_maps      HOST array of n_ops DEVICE pointers (or NULL entries = identity): row_maps[i][r]
+ *                 is the row of operand i that output row r uses (how the caller expresses
+ *                 broadcasting over leading dimensions); rows_out entries each
+ *   conj_mask     bit i set: operand i's spectrum is conjugated (correlation instead of convolution)
+ *   scale         applied to the result (1 for norm=None; the caller folds norm="ortho"/"forward" in)
+ *   out           (rows_out, n)
+ * Internally a power-of-two transform of at least the full linear length is used and the result is
+ * wrapped onto period 2n, so 3- and 4-operand products alias exactly as the reference's do. */
+int mpb200_fft_convolve(const float* const* operands, const int32_t* const* row_maps,
+                        const int32_t* operand_rows, int n_ops, int rows_out, int n, int conj_mask,
+                        float scale, float* out, void* stream);
+
+/* out = irfft(keep bins [bin_lo, bin_hi) of rfft(x, norm="ortho"), n=n_out, norm="ortho") per row;
+ * x is (rows, n_in), out (rows, n_out), both lengths powers of two >= 256 -- the band split of
+ * modules/decompose.py:5-33 (fft_frequency_decompose) and the zero-stuffing resample of :36-73
+ * (fft_resample; its tukey(alpha=0) window is identically one). */
+int mpb200_spectral_band(const float* x, int rows, int n_in, float* out, int n_out, int bin_lo, int bin_hi,
+                         void* stream);
 
 #ifdef __cplusplus
 }

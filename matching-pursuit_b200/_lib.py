@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libmpb200.so")
 SOURCES = ["mpb200.cu", "fftconv.cu"]
-HEADERS = ["kernels.cuh", "fft_core.cuh", "types.h", "plan.h"]
+HEADERS = ["kernels.cuh", "fft_core.cuh", "bigfft.cuh", "types.h", "plan.h"]
 
 MODE_AUTO, MODE_RECORRELATE, MODE_GRAM, MODE_FULL = 0, 1, 2, 3
 MODES = {"auto": MODE_AUTO, "recorrelate": MODE_RECORRELATE, "gram": MODE_GRAM, "full": MODE_FULL}
@@ -70,6 +70,7 @@ _SIGNATURES = {
     "mpb200_plan_timing_enable": (_i, [_p, _i]),
     "mpb200_plan_timing_read": (_i, [_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "mpb200_plan_set_dictionary": (_i, [_p, _p, _p]),
+    "mpb200_plan_set_dictionary_raw": (_i, [_p, _p, _p]),
     "mpb200_plan_get_unit_dictionary": (_i, [_p, _p, _p]),
     "mpb200_sparse_code": (_i, [_p, _p, _i, _i, _p, _p, _p, _p, _p]),
     "mpb200_sparse_code_host": (_i, [_p, _p, _i, _i, _p, _p, _p, _p, _p]),
@@ -86,7 +87,8 @@ _SIGNATURES = {
     "mpb200_subtract": (_i, [_p, _i, _i, _p, _i, _i, _p, _p]),
     "mpb200_gather_atoms": (_i, [_p, _p, _i, _i, _p, _p, _i, _p]),
     "mpb200_unit_norm": (_i, [_p, _p, _i, _i, C.c_float, _p]),
-    "mpb200_fft_convolve": (_i, [_p, _i, _p, _i, _i, _i, _p, _p]),
+    "mpb200_fft_convolve": (_i, [_p, _p, _p, _i, _i, _i, _i, C.c_float, _p, _p]),
+    "mpb200_spectral_band": (_i, [_p, _i, _i, _p, _i, _i, _i, _p]),
 }
 EXPORTED = tuple(_SIGNATURES)
 

@@ -1,12 +1,273 @@
-// fftconv.cu -- two-operand zero-padded FFT convolution / correlation
-// (modules/fft.py:23-35, modules/transfer.py:548-569).
+// fftconv.cu -- FFT helpers around the pursuit, behind the C ABI of include/mpb200.h:
+//   mpb200_fft_convolve   modules/fft.py:23-35 (N-ary zero-padded FFT convolution; also
+//                         modules/transfer.py:548-569) -- spectra product fused into the inverse
+//   mpb200_spectral_band  modules/decompose.py:5-33, 36-73 (ortho rfft -> keep a band of bins ->
+//                         ortho irfft at another length)
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
 #include "../../include/mpb200.h"
+#include "bigfft.cuh"
 #include "plan.h"
+
+namespace mpb {
+
+extern std::atomic<unsigned long long> g_launches;
+
+#define BF_CUDA(expr)                                                                           \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return fail(MPB200_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+    } while (0)
+#define BF_LAUNCH(name)                                                                         \
+    do {                                                                                        \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                     \
+        cudaError_t _e = cudaGetLastError();                                                    \
+        if (_e != cudaSuccess)                                                                  \
+            return fail(MPB200_ECUDA, std::string("launch ") + name + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+// ---- twiddle tables, cached per (device, size), never freed -----------------
+struct BfTables {
+    C32* twL = nullptr;   // exp(+2 pi i t / L), t < L
+    C32* tw1 = nullptr;   // BlockFft<L2> tables
+    C32* tw2 = nullptr;
+};
+static std::mutex g_tab_mutex;
+static std::map<std::pair<int, long long>, C32*> g_tab;   // (device, key) -> device pointer
+
+static int upload(int dev, long long key, const std::vector<C32>& host, C32** out) {
+    auto it = g_tab.find({dev, key});
+    if (it != g_tab.end()) { *out = it->second; return MPB200_OK; }
+    C32* p = nullptr;
+    BF_CUDA(cudaMalloc((void**)&p, host.size() * sizeof(C32)));
+    BF_CUDA(cudaMemcpy(p, host.data(), host.size() * sizeof(C32), cudaMemcpyHostToDevice));
+    g_tab[{dev, key}] = p;
+    *out = p;
+    return MPB200_OK;
+}
+
+static int get_tables(const BfGeom& g, BfTables* t) {
+    std::lock_guard<std::mutex> lock(g_tab_mutex);
+    int dev = 0;
+    BF_CUDA(cudaGetDevice(&dev));
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    int rc;
+    if (g_tab.find({dev, (long long)g.L}) == g_tab.end()) {
+        std::vector<C32> h((size_t)g.L);
+        for (int i = 0; i < g.L; ++i) {
+            long double a = two_pi * (long double)i / (long double)g.L;
+            h[i] = {(float)cosl(a), (float)sinl(a)};
+        }
+        if ((rc = upload(dev, g.L, h, &t->twL))) return rc;
+    } else {
+        t->twL = g_tab[{dev, (long long)g.L}];
+    }
+    const long long k1 = (1LL << 40) + g.L2, k2 = (2LL << 40);
+    if (g_tab.find({dev, k1}) == g_tab.end()) {
+        const int R1 = g.L2 / 256;
+        std::vector<C32> h((size_t)g.L2);
+        for (int m1 = 0; m1 < R1; ++m1)
+            for (int c = 0; c < 256; ++c) {
+                long double a = two_pi * (long double)(((long long)c * m1) % g.L2) / (long double)g.L2;
+                h[(size_t)m1 * 256 + c] = {(float)cosl(a), (float)sinl(a)};
+            }
+        if ((rc = upload(dev, k1, h, &t->tw1))) return rc;
+    } else {
+        t->tw1 = g_tab[{dev, k1}];
+    }
+    if (g_tab.find({dev, k2}) == g_tab.end()) {
+        std::vector<C32> h(256);
+        for (int m2 = 0; m2 < 16; ++m2)
+            for (int j3 = 0; j3 < 16; ++j3) {
+                long double a = two_pi * (long double)((j3 * m2) % 256) / 256.0L;
+                h[m2 * 16 + j3] = {(float)cosl(a), (float)sinl(a)};
+            }
+        if ((rc = upload(dev, k2, h, &t->tw2))) return rc;
+    } else {
+        t->tw2 = g_tab[{dev, k2}];
+    }
+    return MPB200_OK;
+}
+
+static bool make_geom(long long L, BfGeom* g) {
+    if (L < 256 || L > (1 << 18) || (L & (L - 1))) return false;
+    int L2 = L < 4096 ? (int)L : 4096;
+    int R = (int)(L / L2);
+    if (R > 32) { L2 = 8192; R = (int)(L / L2); }
+    g->L = (int)L; g->R = R; g->L2 = L2;
+    return true;
+}
+
+static long long pow2_at_least(long long v) {
+    long long p = 256;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+#define BF_DISPATCH_R(r, ...)                                        \
+    switch (r) {                                                     \
+        case 1: { constexpr int RR = 1; __VA_ARGS__; } break;        \
+        case 2: { constexpr int RR = 2; __VA_ARGS__; } break;        \
+        case 4: { constexpr int RR = 4; __VA_ARGS__; } break;        \
+        case 8: { constexpr int RR = 8; __VA_ARGS__; } break;        \
+        case 16: { constexpr int RR = 16; __VA_ARGS__; } break;      \
+        case 32: { constexpr int RR = 32; __VA_ARGS__; } break;      \
+        default: return fail(MPB200_EINVAL, "unsupported radix");    \
+    }
+#define BF_DISPATCH_L2(m, ...)                                       \
+    switch (m) {                                                     \
+        case 256: { constexpr int MM = 256; __VA_ARGS__; } break;    \
+        case 512: { constexpr int MM = 512; __VA_ARGS__; } break;    \
+        case 1024: { constexpr int MM = 1024; __VA_ARGS__; } break;  \
+        case 2048: { constexpr int MM = 2048; __VA_ARGS__; } break;  \
+        case 4096: { constexpr int MM = 4096; __VA_ARGS__; } break;  \
+        case 8192: { constexpr int MM = 8192; __VA_ARGS__; } break;  \
+        default: return fail(MPB200_EINVAL, "unsupported row FFT size"); \
+    }
+
+static int launch_cols_fwd(const BfGeom& g, const BfTables& t, const float* x, int n, long long stride, int rows,
+                           C32* y, cudaStream_t st) {
+    dim3 grid((g.L2 + 255) / 256, rows);
+    BF_DISPATCH_R(g.R, (k_bf_cols_fwd<RR><<<grid, 256, 0, st>>>(x, n, stride, g.L2, t.twL, y)));
+    BF_LAUNCH("k_bf_cols_fwd");
+    return MPB200_OK;
+}
+
+template <int DIR>
+static int launch_rows(const BfGeom& g, const BfTables& t, BfRowsArgs a, cudaStream_t st) {
+    a.R = g.R;
+    a.twL = t.twL;
+    a.tw1 = t.tw1;
+    a.tw2 = t.tw2;
+    BF_DISPATCH_L2(g.L2, {
+        using F = BlockFft<MM, float>;
+        constexpr int TPB = F::T < 128 ? 128 : F::T;
+        constexpr int NT = TPB / F::T;
+        const size_t smem = (size_t)(256 + NT * F::SMEM_CPX) * sizeof(C32);
+        static bool once = false;
+        if (!once) {
+            BF_CUDA(cudaFuncSetAttribute(k_bf_rows<MM, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            once = true;
+        }
+        k_bf_rows<MM, DIR><<<(a.n_transforms + NT - 1) / NT, TPB, smem, st>>>(a);
+    });
+    BF_LAUNCH("k_bf_rows");
+    return MPB200_OK;
+}
+
+static int launch_cols_inv(const BfGeom& g, const C32* s, int rows, float scale, int n_keep, long long out_stride,
+                           float* out, cudaStream_t st) {
+    dim3 grid((g.L2 + 255) / 256, rows);
+    BF_DISPATCH_R(g.R, (k_bf_cols_inv<RR><<<grid, 256, 0, st>>>(s, g.L2, scale, n_keep, out_stride, out)));
+    BF_LAUNCH("k_bf_cols_inv");
+    return MPB200_OK;
+}
+
+// forward transform of real rows into a fresh stream-ordered buffer (permuted layout)
+static int forward_real(const BfGeom& g, const BfTables& t, const float* x, int n, int rows, C32** spec,
+                        cudaStream_t st) {
+    BF_CUDA(cudaMallocAsync((void**)spec, (size_t)rows * g.L * sizeof(C32), st));
+    int rc = launch_cols_fwd(g, t, x, n, n, rows, *spec, st);
+    if (rc) return rc;
+    BfRowsArgs a = {};
+    a.ops[0] = *spec;
+    a.n_ops = 1;
+    a.n_transforms = rows * g.R;
+    a.dst = *spec;   // in place: a CTA reads its whole row before it writes
+    return launch_rows<-1>(g, t, a, st);
+}
+
+}  // namespace mpb
 
 using namespace mpb;
 
-extern "C" int mpb200_fft_convolve(const float* a, int rows_a, const float* b, int rows_b, int n, int conjugate_b,
-                                   float* out, void* stream) {
-    (void)a; (void)rows_a; (void)b; (void)rows_b; (void)n; (void)conjugate_b; (void)out; (void)stream;
-    return fail(MPB200_EINVAL, "mpb200_fft_convolve: not built into this library version");
+extern "C" int mpb200_fft_convolve(const float* const* operands, const int32_t* const* row_maps,
+                                   const int32_t* operand_rows, int n_ops, int rows_out, int n, int conj_mask,
+                                   float scale, float* out, void* stream) {
+    if (!operands || !operand_rows || !out || n_ops < 1 || n_ops > BF_MAX_OPS || rows_out < 1 || n < 1)
+        return fail(MPB200_EINVAL, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long lin = (long long)n_ops * n - n_ops + 1;      // length of the full linear product
+    const long long W = 2LL * n;                                 // the reference's circular length
+    BfGeom g;
+    if (!make_geom(pow2_at_least(lin > W ? lin : W), &g))
+        return fail(MPB200_EINVAL, "fft_convolve: length too large (n_ops * n must stay below 2^18)");
+    BfTables t;
+    int rc = get_tables(g, &t);
+    if (rc) return rc;
+    C32* spec[BF_MAX_OPS] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < n_ops; ++i) {
+        if (!operands[i] || operand_rows[i] < 1) return fail(MPB200_EINVAL, "null operand");
+        rc = forward_real(g, t, operands[i], n, operand_rows[i], &spec[i], st);
+        if (rc) return rc;
+    }
+    C32* s = nullptr;
+    BF_CUDA(cudaMallocAsync((void**)&s, (size_t)rows_out * g.L * sizeof(C32), st));
+    BfRowsArgs a = {};
+    for (int i = 0; i < n_ops; ++i) {
+        a.ops[i] = spec[i];
+        a.rowmap[i] = row_maps ? row_maps[i] : nullptr;
+    }
+    a.conj_mask = conj_mask;
+    a.n_ops = n_ops;
+    a.n_transforms = rows_out * g.R;
+    a.dst = s;
+    rc = launch_rows<1>(g, t, a, st);
+    if (rc) return rc;
+    const float total_scale = scale / (float)g.L;
+    if (lin <= W) {
+        rc = launch_cols_inv(g, s, rows_out, total_scale, n, n, out, st);
+        if (rc) return rc;
+    } else {
+        float* full = nullptr;
+        BF_CUDA(cudaMallocAsync((void**)&full, (size_t)rows_out * g.L * sizeof(float), st));
+        rc = launch_cols_inv(g, s, rows_out, total_scale, g.L, g.L, full, st);
+        if (rc) return rc;
+        k_bf_wrap<<<dim3((n + 255) / 256, rows_out), 256, 0, st>>>(full, g.L, (int)W, n, out);
+        BF_LAUNCH("k_bf_wrap");
+        BF_CUDA(cudaFreeAsync(full, st));
+    }
+    BF_CUDA(cudaFreeAsync(s, st));
+    for (int i = 0; i < n_ops; ++i) BF_CUDA(cudaFreeAsync(spec[i], st));
+    return MPB200_OK;
+}
+
+extern "C" int mpb200_spectral_band(const float* x, int rows, int n_in, float* out, int n_out, int bin_lo,
+                                    int bin_hi, void* stream) {
+    if (!x || !out || rows < 1) return fail(MPB200_EINVAL, "bad argument");
+    BfGeom gi, go;
+    if (!make_geom(n_in, &gi) || !make_geom(n_out, &go))
+        return fail(MPB200_EINVAL, "spectral_band: lengths must be powers of two in [256, 2^18]");
+    if (bin_lo < 0 || bin_hi < bin_lo) return fail(MPB200_EINVAL, "bad bin range");
+    cudaStream_t st = (cudaStream_t)stream;
+    BfTables ti, to;
+    int rc = get_tables(gi, &ti);
+    if (!rc) rc = get_tables(go, &to);
+    if (rc) return rc;
+    C32* spec = nullptr;
+    rc = forward_real(gi, ti, x, n_in, rows, &spec, st);
+    if (rc) return rc;
+    C32* band = nullptr;
+    BF_CUDA(cudaMallocAsync((void**)&band, (size_t)rows * go.L * sizeof(C32), st));
+    k_bf_band<<<dim3((n_out + 255) / 256, rows), 256, 0, st>>>(spec, n_in, gi.R, gi.L2, band, n_out, go.R, go.L2,
+                                                              bin_lo, bin_hi);
+    BF_LAUNCH("k_bf_band");
+    BfRowsArgs a = {};
+    a.ops[0] = band;
+    a.n_ops = 1;
+    a.n_transforms = rows * go.R;
+    a.dst = band;
+    rc = launch_rows<1>(go, to, a, st);
+    if (rc) return rc;
+    const float scale = (float)(1.0 / std::sqrt((double)n_in * (double)n_out));
+    rc = launch_cols_inv(go, band, rows, scale, n_out, n_out, out, st);
+    if (rc) return rc;
+    BF_CUDA(cudaFreeAsync(band, st));
+    BF_CUDA(cudaFreeAsync(spec, st));
+    return MPB200_OK;
 }

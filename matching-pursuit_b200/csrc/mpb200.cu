@@ -451,19 +451,31 @@ int mpb200_plan_timing_read(mpb200_plan_t plan, double* ms_by_tag, int64_t* coun
     return MPB200_OK;
 }
 
-int mpb200_plan_set_dictionary(mpb200_plan_t plan, const float* d, void* stream) {
+static int set_dictionary_impl(mpb200_plan_t plan, const float* d, bool normalize, void* stream) {
     Plan* p = reinterpret_cast<Plan*>(plan);
     int rc = check_plan(p, false);
     if (rc) return rc;
     if (!d) return fail(MPB200_EINVAL, "null dictionary");
     cudaStream_t st = (cudaStream_t)stream;
-    k_unit_norm<<<(p->K + 7) / 8, 256, 0, st>>>(d, p->dict, p->K, p->A, 1e-8f);
-    MPB_LAUNCH_CHECK("k_unit_norm");
+    if (normalize) {
+        k_unit_norm<<<(p->K + 7) / 8, 256, 0, st>>>(d, p->dict, p->K, p->A, 1e-8f);
+        MPB_LAUNCH_CHECK("k_unit_norm");
+    } else {
+        MPB_CUDA(cudaMemcpyAsync(p->dict, d, (size_t)p->K * p->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
     rc = build_pair_spectra(p, st);
     if (rc) return rc;
     p->dict_set = true;
     p->cur_batch = 0;
     return MPB200_OK;
+}
+
+int mpb200_plan_set_dictionary(mpb200_plan_t plan, const float* d, void* stream) {
+    return set_dictionary_impl(plan, d, true, stream);
+}
+
+int mpb200_plan_set_dictionary_raw(mpb200_plan_t plan, const float* d, void* stream) {
+    return set_dictionary_impl(plan, d, false, stream);
 }
 
 int mpb200_plan_get_unit_dictionary(mpb200_plan_t plan, float* out, void* stream) {

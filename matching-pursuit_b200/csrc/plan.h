@@ -1,5 +1,6 @@
 // plan.h -- host-side state behind an mpb200_plan_t.
 #pragma once
+#include <atomic>
 #include <cstddef>
 #include <cstdint>
 #include <string>

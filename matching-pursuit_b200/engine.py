@@ -91,16 +91,17 @@ class Plan:
         return {"first_pass": (ms[1], cnt[1]), "apply": (ms[2], cnt[2]), "recorrelate": (ms[3], cnt[3])}
 
     # ---- dictionary -----------------------------------------------------
-    def set_dictionary(self, d: torch.Tensor) -> "Plan":
+    def set_dictionary(self, d: torch.Tensor, normalize: bool = True) -> "Plan":
         """``d`` is (K, A) (or (K, 1, A)); it is unit-normed on the device
-        exactly like modules/normalization.py:4-6 and not modified."""
+        exactly like modules/normalization.py:4-6 (unless ``normalize`` is
+        False: atoms used as given) and not modified."""
         d = _dev_f32(d, self.device).reshape(d.shape[0], -1)
         if tuple(d.shape) != (self.n_atoms, self.atom_size):
             raise MpbError(f"dictionary shape {tuple(d.shape)} does not match the plan "
                            f"({self.n_atoms}, {self.atom_size})")
         with torch.cuda.device(self.device):
-            check(self._lib.mpb200_plan_set_dictionary(self._h, _ptr(d), _stream_ptr(self.device)),
-                  "mpb200_plan_set_dictionary")
+            fn = self._lib.mpb200_plan_set_dictionary if normalize else self._lib.mpb200_plan_set_dictionary_raw
+            check(fn(self._h, _ptr(d), _stream_ptr(self.device)), "mpb200_plan_set_dictionary")
         self._keep = d  # stream-ordered use: keep alive until the next call replaces it
         return self
 
