@@ -56,7 +56,7 @@ def parse_args():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (marks the run non-standard)")
     ap.add_argument("--iterations", type=int, default=0, help="override the iteration count (non-standard)")
-    ap.add_argument("--mode", default="recorrelate")
+    ap.add_argument("--mode", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU time of the cpu_baseline sample")

@@ -76,6 +76,11 @@ int mpb200_plan_create(mpb200_plan_t* plan, int n_atoms, int atom_size, int n_sa
                        int mode, int atom_lo, int atom_hi, uint64_t gram_budget_bytes);
 int mpb200_plan_destroy(mpb200_plan_t plan);
 int mpb200_plan_info_get(mpb200_plan_t plan, mpb200_plan_info* info);
+/* Options.  MPB200_OPT_REFRESH_EVERY (GRAM mode): re-correlate the whole map from
+ * the residual every `value` iterations to bound the drift of the incremental
+ * fp32 updates (0 = never, the default). */
+#define MPB200_OPT_REFRESH_EVERY 1
+int mpb200_plan_set_option(mpb200_plan_t plan, int option, long long value);
 
 /* Per-kernel device timing of the pursuit loop (bench / profiling aid, no
  * reference counterpart).  While enabled, mpb200_sparse_code records a CUDA

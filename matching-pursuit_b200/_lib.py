@@ -67,6 +67,7 @@ _SIGNATURES = {
     "mpb200_plan_create": (_i, [C.POINTER(_p), _i, _i, _i, _i, _i, _i, _i, C.c_uint64]),
     "mpb200_plan_destroy": (_i, [_p]),
     "mpb200_plan_info_get": (_i, [_p, C.POINTER(PlanInfo)]),
+    "mpb200_plan_set_option": (_i, [_p, _i, C.c_longlong]),
     "mpb200_plan_timing_enable": (_i, [_p, _i]),
     "mpb200_plan_timing_read": (_i, [_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "mpb200_plan_set_dictionary": (_i, [_p, _p, _p]),

@@ -417,6 +417,13 @@ struct ApplyArgs {
     const C32* tw2;
     C32* winspec;         // (B, M)
     int do_fft;           // 0 on the last step
+    // GRAM mode: winners whose atom fits inside the signal are handed to k_gram_update through
+    // `upd`; the others (atom truncated at the right edge: the Gram identity does not hold,
+    // SURVEY.md A.3) take the FFT route through a compacted window list.
+    int gram;
+    GramUpdate* upd;      // (B)
+    int* trunc_count;     // [2]: counter of this iteration at [step & 1]; the other one is reset here
+    int parity;
 };
 
 template <int M, bool SELECT>
@@ -451,9 +458,28 @@ k_apply(const ApplyArgs a) {
     wi.blk0 = first >> a.blk_shift;
     wi.t0 = wi.blk0 << a.blk_shift;
     wi.nvb = (last >> a.blk_shift) - wi.blk0 + 1;
-    if (threadIdx.x == 0) a.win[b] = wi;
+    int slot = b;
+    bool fft = a.do_fft != 0;
+    if (a.gram) {
+        __shared__ int s_slot;
+        const bool truncated = p + a.A > a.N;
+        if (threadIdx.x == 0) {
+            GramUpdate u;
+            u.value = w.value;
+            u.atom = w.atom;
+            u.position = p;
+            u.valid = truncated ? 0 : 1;
+            a.upd[b] = u;
+            s_slot = truncated ? atomicAdd(a.trunc_count + a.parity, 1) : -1;
+            if (b == 0) a.trunc_count[a.parity ^ 1] = 0;   // nobody touches the other counter in this launch
+        }
+        __syncthreads();
+        slot = s_slot;
+        fft = fft && truncated;
+    }
+    if (threadIdx.x == 0 && slot >= 0) a.win[slot] = wi;
     __syncthreads();  // residual writes of this CTA are visible to its own loads below
-    if (a.do_fft) {
+    if (fft) {
         const int tl = threadIdx.x;
         C32 rr[F::E];
         if (tl < F::T) {
@@ -469,10 +495,96 @@ k_apply(const ApplyArgs a) {
         __syncthreads();
         if (tl < F::T) {
             F::template pass3<-1>(rr, tl, sm);
-            C32* out = a.winspec + (size_t)b * M;
+            C32* out = a.winspec + (size_t)slot * M;
 #pragma unroll
             for (int e = 0; e < F::E; ++e) out[F::out_index(tl, e)] = rr[e];
         }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// GRAM mode update.  One warp per (signal b, owned atom j):
+//     map[b, j, t] -= v * G[k*, j, t - p + A - 1]      for t in the +-A window of the winner
+// (fused multiply-add, one rounding), then the (max, argmax) of every touched block and of the
+// whole row.  Pure streaming: 4 bytes of G read + 8 bytes of map read-modify-written per position.
+// gram is (K, nloc, GS) with GS >= 2A-1; G[k, j, l] = sum_i d_k[i + l - (A-1)] * d_j[i].
+// ---------------------------------------------------------------------------
+struct GramArgs {
+    float* map;            // (B, nloc, N)
+    const float* gram;     // (K, nloc, GS)
+    const GramUpdate* upd; // (B)
+    float* bm_val;
+    int* bm_pos;
+    float* row_val;
+    int* row_pos;
+    int rows;              // B * nloc
+    int nloc, N, NB, blk_shift, A, GS;
+};
+
+__global__ void __launch_bounds__(256)
+k_gram_update(const GramArgs a) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= a.rows) return;
+    const int b = row / a.nloc, j = row - b * a.nloc;
+    const GramUpdate u = a.upd[b];
+    if (!u.valid) return;
+    const int p = u.position, blk = 1 << a.blk_shift;
+    const float nv = -u.value;
+    const int first = max(0, p - a.A + 1), last = min(a.N - 1, p + a.A - 1);
+    const int blk0 = first >> a.blk_shift, nvb = (last >> a.blk_shift) - blk0 + 1;   // nvb <= 32
+    const float* __restrict__ g = a.gram + ((size_t)u.atom * a.nloc + j) * a.GS + (a.A - 1 - p);   // g[t]
+    float* __restrict__ m = a.map + (size_t)row * a.N;
+    const size_t bm0 = (size_t)row * a.NB;
+    float my_v = -INFINITY;
+    int my_p = INT_MAX;
+    for (int i = 0; i < nvb; ++i) {
+        const int tb = (blk0 + i) << a.blk_shift;
+        float best = -INFINITY;
+        int at = INT_MAX;
+        for (int t = tb + lane; t < tb + blk && t < a.N; t += 32) {
+            float x = m[t];
+            if (t >= first && t <= last) {
+                x = fmaf(nv, __ldg(g + t), x);
+                m[t] = x;
+            }
+            if (x > best) {
+                best = x;
+                at = t;
+            }
+        }
+        warp_argmax(best, at);
+        if (lane == i) {
+            my_v = best;
+            my_p = at;
+        }
+        if (lane == 0) {
+            a.bm_val[bm0 + blk0 + i] = best;
+            a.bm_pos[bm0 + blk0 + i] = at;
+        }
+    }
+    // row maximum over all NB blocks: refreshed ones from registers, the rest from the table
+    float v = -INFINITY;
+    int bi_best = INT_MAX;
+    for (int q = 0; q * 32 < a.NB; ++q) {
+        const int bi = q * 32 + lane;
+        const int src = bi - blk0;
+        const bool fresh = src >= 0 && src < nvb;
+        const float fv = __shfl_sync(0xffffffffu, my_v, fresh ? src : 0);
+        float c = -INFINITY;
+        if (bi < a.NB) c = fresh ? fv : a.bm_val[bm0 + bi];
+        if (c > v) {
+            v = c;
+            bi_best = bi;
+        }
+    }
+    warp_argmax(v, bi_best);
+    const int src = bi_best - blk0;
+    const bool fresh = bi_best != INT_MAX && src >= 0 && src < nvb;
+    const int fp = __shfl_sync(0xffffffffu, my_p, fresh ? src : 0);
+    if (lane == 0) {
+        a.row_val[row] = v;
+        a.row_pos[row] = (bi_best == INT_MAX) ? 0 : (fresh ? fp : a.bm_pos[bm0 + bi_best]);
     }
 }
 

@@ -170,7 +170,7 @@ static CorrArgs base_corr_args(const Plan* p) {
 
 // Full correlation of the current residual: block maxima (and the dense map
 // when `dense` is given) for all positions, in slabs of at most wcap windows.
-static int full_pass(Plan* p, int batch, float* dense, cudaStream_t st) {
+static int full_pass(Plan* p, int batch, float* dense, cudaStream_t st, bool with_maxima = false) {
     const int total = batch * p->nchunks;
     for (int w0 = 0; w0 < total; w0 += p->wcap) {
         const int n = total - w0 < p->wcap ? total - w0 : p->wcap;
@@ -184,13 +184,14 @@ static int full_pass(Plan* p, int batch, float* dense, cudaStream_t st) {
             a.dense_row_stride = (long long)p->nloc * p->N;
             a.dense_atom_stride = p->N;
             a.dense_col_off = 0;
-            rc = launch_corr<MODE_DENSE>(p, a, corr_groups(p, n), st);
+            if (with_maxima) rc = launch_corr<MODE_DENSE | MODE_BLOCKMAX>(p, a, corr_groups(p, n), st);
+            else rc = launch_corr<MODE_DENSE>(p, a, corr_groups(p, n), st);
         } else {
             rc = launch_corr<MODE_BLOCKMAX>(p, a, corr_groups(p, n), st);
         }
         if (rc) return rc;
     }
-    if (!dense) {
+    if (!dense || with_maxima) {
         const int rows = batch * p->nloc;
         k_rowmax<<<(rows + 7) / 8, 256, 0, st>>>(p->bm_val, p->bm_pos, rows, p->NB, p->row_val, p->row_pos);
         MPB_LAUNCH_CHECK("k_rowmax");
@@ -224,6 +225,10 @@ static int launch_apply(Plan* p, int batch, const Best* winner, int step, int n_
     a.tw2 = p->tw2;
     a.winspec = p->winspec;
     a.do_fft = do_fft;
+    a.gram = p->mode == MPB200_MODE_GRAM;
+    a.upd = p->upd;
+    a.trunc_count = p->trunc_count;
+    a.parity = (int)(p->iter & 1u);
     MPB_DISPATCH_M(p->M, {
         using F = BlockFft<MM, float>;
         const size_t smem = (size_t)(F::SMEM_CPX + 256) * sizeof(C32);
@@ -235,13 +240,73 @@ static int launch_apply(Plan* p, int batch, const Best* winner, int step, int n_
     return MPB200_OK;
 }
 
-// Refresh the block maxima (and row maxima) of the windows written by k_apply.
+// Refresh the map / block maxima / row maxima after k_apply's subtraction.
 static int step_refresh(Plan* p, int batch, cudaStream_t st) {
-    if (p->mode == MPB200_MODE_FULL) return full_pass(p, batch, nullptr, st);
-    CorrArgs a = base_corr_args(p);
-    a.win = p->win_step;
-    a.nwin = batch;
-    return launch_corr<MODE_BLOCKMAX | MODE_ROWMAX>(p, a, corr_groups(p, batch), st);
+    int rc = MPB200_OK;
+    if (p->mode == MPB200_MODE_FULL) {
+        rc = full_pass(p, batch, nullptr, st);
+    } else if (p->mode == MPB200_MODE_GRAM) {
+        const bool refresh = p->refresh_every > 0 && (p->iter + 1) % (unsigned)p->refresh_every == 0;
+        if (refresh) {
+            rc = full_pass(p, batch, p->map, st, true);
+        } else {
+            GramArgs g;
+            g.map = p->map;
+            g.gram = p->gram;
+            g.upd = p->upd;
+            g.bm_val = p->bm_val;
+            g.bm_pos = p->bm_pos;
+            g.row_val = p->row_val;
+            g.row_pos = p->row_pos;
+            g.rows = batch * p->nloc;
+            g.nloc = p->nloc;
+            g.N = p->N;
+            g.NB = p->NB;
+            g.blk_shift = p->blk_shift;
+            g.A = p->A;
+            g.GS = p->GS;
+            k_gram_update<<<(g.rows + 7) / 8, 256, 0, st>>>(g);
+            MPB_LAUNCH_CHECK("k_gram_update");
+            // winners truncated at the right edge: FFT re-correlation of their windows, written into the map
+            CorrArgs a = base_corr_args(p);
+            a.win = p->win_step;
+            a.nwin = batch;
+            a.nwin_ptr = p->trunc_count + (p->iter & 1u);
+            a.dense = p->map;
+            a.dense_row_stride = (long long)p->nloc * p->N;
+            a.dense_atom_stride = p->N;
+            a.dense_col_off = 0;
+            rc = launch_corr<MODE_DENSE | MODE_BLOCKMAX | MODE_ROWMAX>(p, a, corr_groups(p, batch), st);
+        }
+    } else {
+        CorrArgs a = base_corr_args(p);
+        a.win = p->win_step;
+        a.nwin = batch;
+        rc = launch_corr<MODE_BLOCKMAX | MODE_ROWMAX>(p, a, corr_groups(p, batch), st);
+    }
+    p->iter++;
+    return rc;
+}
+
+// Gram table: correlation of every atom (left-padded by A-1 zeros) with every owned atom,
+// through the same window FFT + pair-spectrum machinery:  gram[k][j][l] = sum_i d_k[i + l - (A-1)] d_j[i].
+static int build_gram(Plan* p, cudaStream_t st) {
+    for (int k0 = 0; k0 < p->K; k0 += p->wcap) {
+        const int n = p->K - k0 < p->wcap ? p->K - k0 : p->wcap;
+        int rc = launch_window_fft(p, p->dict, p->A, p->A, p->win_gram + k0, n, p->winspec, st);
+        if (rc) return rc;
+        CorrArgs a = base_corr_args(p);
+        a.win = p->win_gram + k0;
+        a.nwin = n;
+        a.len = p->A;                      // valid outputs: t0 + m < len  <=>  m < 2A-1   (t0 = -(A-1))
+        a.dense = p->gram;
+        a.dense_row_stride = (long long)p->nloc * p->GS;
+        a.dense_atom_stride = p->GS;
+        a.dense_col_off = p->A - 1;        // column = t0 + m + (A-1) = m
+        rc = launch_corr<MODE_DENSE>(p, a, corr_groups(p, n), st);
+        if (rc) return rc;
+    }
+    return MPB200_OK;
 }
 
 static int build_pair_spectra(Plan* p, cudaStream_t st) {
@@ -333,15 +398,19 @@ int mpb200_plan_create(mpb200_plan_t* out, int n_atoms, int atom_size, int n_sam
     const uint64_t gram_bytes = (uint64_t)n_atoms * p->nloc * (2ull * atom_size) * sizeof(float);
     const uint64_t map_bytes = (uint64_t)max_batch * p->nloc * n_samples * sizeof(float);
     if (mode == MPB200_MODE_AUTO) {
-        // GRAM pays off when the table and the resident map fit comfortably; it is not built yet,
-        // so AUTO resolves to windowed re-correlation for now.
-        (void)gram_bytes; (void)map_bytes; (void)gram_budget_bytes;
-        mode = MPB200_MODE_RECORRELATE;
+        // GRAM when the table and the resident map fit AND the table build (K window transforms per
+        // pair) is amortised by the batch: break-even is about K / max_batch iterations.
+        size_t free_b = 0, total_b = 0;
+        MPB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const uint64_t budget = gram_budget_bytes ? gram_budget_bytes : (uint64_t)(0.4 * (double)free_b);
+        const bool fits = gram_bytes <= budget && gram_bytes + map_bytes <= (uint64_t)(0.8 * (double)free_b);
+        mode = (fits && (long long)max_batch * 16 >= n_atoms) ? MPB200_MODE_GRAM : MPB200_MODE_RECORRELATE;
     }
     p->mode = mode;
-    if (mode == MPB200_MODE_GRAM) {
+    p->GS = 2 * atom_size;
+    if (mode == MPB200_MODE_GRAM && (2 * atom_size - 2) / p->blk + 2 > 32) {
         free_plan(p);
-        return fail(MPB200_EINVAL, "GRAM mode is not built into this library version");
+        return fail(MPB200_EINVAL, "GRAM mode: window spans more than 32 blocks");
     }
 
     int rc = MPB200_OK;
@@ -378,6 +447,24 @@ int mpb200_plan_create(mpb200_plan_t* out, int n_atoms, int atom_size, int n_sam
     MPB_TRY(dev_alloc(p, &p->row_pos, (size_t)max_batch * p->nloc));
     MPB_TRY(dev_alloc(p, &p->residual, (size_t)max_batch * n_samples));
     MPB_TRY(dev_alloc(p, &p->best, (size_t)max_batch));
+    std::vector<Win> wg;
+    if (mode == MPB200_MODE_GRAM) {
+        p->gram_bytes = gram_bytes;
+        MPB_TRY(dev_alloc(p, &p->gram, (size_t)n_atoms * p->nloc * p->GS));
+        MPB_TRY(dev_alloc(p, &p->map, (size_t)max_batch * p->nloc * n_samples));
+        MPB_TRY(dev_alloc(p, &p->upd, (size_t)max_batch));
+        MPB_TRY(dev_alloc(p, &p->trunc_count, (size_t)2));
+        MPB_TRY(dev_alloc(p, &p->win_gram, (size_t)n_atoms));
+        wg.resize((size_t)n_atoms);
+        for (int k = 0; k < n_atoms; ++k) {
+            Win w;
+            w.row = k;
+            w.t0 = -(atom_size - 1);
+            w.blk0 = 0;
+            w.nvb = (2 * atom_size - 1 + p->blk - 1) / p->blk;
+            wg[(size_t)k] = w;
+        }
+    }
 #undef MPB_TRY
     cudaError_t e = cudaSuccess;
     auto up = [&](void* dst, const void* src, size_t bytes) {
@@ -388,6 +475,8 @@ int mpb200_plan_create(mpb200_plan_t* out, int n_atoms, int atom_size, int n_sam
     up(p->tw1d, t1d.data(), t1d.size() * sizeof(t1d[0]));
     up(p->tw2d, t2d.data(), t2d.size() * sizeof(t2d[0]));
     up(p->win_full, wf.data(), wf.size() * sizeof(Win));
+    if (!wg.empty()) up(p->win_gram, wg.data(), wg.size() * sizeof(Win));
+    if (p->gram && e == cudaSuccess) e = cudaMemset(p->gram, 0, (size_t)n_atoms * p->nloc * p->GS * sizeof(float));
     if (e != cudaSuccess) {
         free_plan(p);
         return fail(MPB200_ECUDA, std::string("table upload: ") + cudaGetErrorString(e));
@@ -465,9 +554,26 @@ static int set_dictionary_impl(mpb200_plan_t plan, const float* d, bool normaliz
     }
     rc = build_pair_spectra(p, st);
     if (rc) return rc;
+    if (p->mode == MPB200_MODE_GRAM) {
+        rc = build_gram(p, st);
+        if (rc) return rc;
+    }
     p->dict_set = true;
     p->cur_batch = 0;
     return MPB200_OK;
+}
+
+int mpb200_plan_set_option(mpb200_plan_t plan, int option, long long value) {
+    Plan* p = reinterpret_cast<Plan*>(plan);
+    if (!p) return fail(MPB200_EINVAL, "null plan");
+    switch (option) {
+        case MPB200_OPT_REFRESH_EVERY:
+            if (value < 0) return fail(MPB200_EINVAL, "refresh_every must be >= 0");
+            p->refresh_every = (int)value;
+            return MPB200_OK;
+        default:
+            return fail(MPB200_EINVAL, "unknown option");
+    }
 }
 
 int mpb200_plan_set_dictionary(mpb200_plan_t plan, const float* d, void* stream) {
@@ -496,6 +602,11 @@ int mpb200_begin(mpb200_plan_t plan, const float* signal, int batch, void* strea
     cudaStream_t st = (cudaStream_t)stream;
     MPB_CUDA(cudaMemcpyAsync(p->residual, signal, (size_t)batch * p->N * sizeof(float), cudaMemcpyDeviceToDevice, st));
     p->cur_batch = batch;
+    p->iter = 0;
+    if (p->mode == MPB200_MODE_GRAM) {
+        MPB_CUDA(cudaMemsetAsync(p->trunc_count, 0, 2 * sizeof(int), st));
+        return full_pass(p, batch, p->map, st, true);
+    }
     return full_pass(p, batch, nullptr, st);
 }
 

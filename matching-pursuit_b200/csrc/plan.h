@@ -35,9 +35,15 @@ struct Plan {
     Best* best = nullptr;           // (Bmax)
 
     // Gram mode
-    float* gram = nullptr;          // (K, nloc, 2A)
+    float* gram = nullptr;          // (K, nloc, GS), GS = 2A
     float* map = nullptr;           // (Bmax, nloc, N)
+    GramUpdate* upd = nullptr;      // (Bmax)
+    int* trunc_count = nullptr;     // [2]
+    Win* win_gram = nullptr;        // (K) windows of the Gram build
+    int GS = 0;
     uint64_t gram_bytes = 0;
+    unsigned iter = 0;              // iterations applied since begin (parity selects trunc_count slot)
+    int refresh_every = 0;          // GRAM: full re-correlation every this many iterations (0 = never)
 
     // staging for the host-buffer entry point
     float* d_signal = nullptr;

@@ -13,6 +13,13 @@ struct Win {
     int nvb;   // number of blocks (of `blk` outputs) that are valid in this window
 };
 
+struct GramUpdate {   // one per signal and iteration (GRAM mode)
+    float value;
+    int atom;      // global atom index
+    int position;
+    int valid;     // 1: apply the Gram update; 0: this signal takes the FFT route
+};
+
 struct Best {  // == mpb200_best
     float value;
     int atom;

@@ -78,6 +78,11 @@ class Plan:
     def close(self):
         self._finalizer()
 
+    def set_refresh_every(self, iterations: int) -> "Plan":
+        """GRAM mode: re-correlate the whole map every ``iterations`` steps (0 = never)."""
+        check(self._lib.mpb200_plan_set_option(self._h, 1, int(iterations)), "mpb200_plan_set_option")
+        return self
+
     # ---- per-kernel timing (bench aid) ----------------------------------
     def timing(self, enable: bool) -> None:
         check(self._lib.mpb200_plan_timing_enable(self._h, int(bool(enable))), "mpb200_plan_timing_enable")

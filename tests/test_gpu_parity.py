@@ -35,7 +35,7 @@ def run_plan(signal, d, steps, mode="recorrelate", atom_range=None):
 # --------------------------------------------------------------------------
 # golden vectors from the live reference
 # --------------------------------------------------------------------------
-@pytest.mark.parametrize("mode", ["recorrelate", "full"])
+@pytest.mark.parametrize("mode", ["recorrelate", "full", "gram"])
 @pytest.mark.parametrize("path", [p for p in SC_CASES if "lcn" not in p],
                          ids=[os.path.basename(p)[:-4] for p in SC_CASES if "lcn" not in p])
 def test_golden_sparse_code(path, mode):
@@ -114,7 +114,7 @@ def make_case(k, a, n, b, s, family):
     return sig, d
 
 
-@pytest.mark.parametrize("mode", ["recorrelate", "full"])
+@pytest.mark.parametrize("mode", ["recorrelate", "full", "gram"])
 @pytest.mark.parametrize("case", CASES, ids=[f"K{c[0]}_A{c[1]}_N{c[2]}_B{c[3]}_{c[5]}" for c in CASES])
 def test_oracle_parity(case, mode):
     k, a, n, b, s, family = case
@@ -123,6 +123,30 @@ def test_oracle_parity(case, mode):
     atom, pos, val, res = run_plan(sig, d, s, mode)
     checked = compare_with_oracle_trace(tr, atom, pos, val, res)
     assert checked > 0
+
+
+@pytest.mark.parametrize("refresh", [0, 50])
+def test_gram_mode_long_run_against_oracle(refresh):
+    """Incremental Gram updates over 300 iterations (drift check), with and without periodic
+    re-correlation; noise signals make a good share of the winners overhang the right edge,
+    which exercises the FFT route inside GRAM mode."""
+    k, a, n, b, s = 128, 256, 8192, 2, 300
+    d = O.make_dictionary(k, a, seed=11)
+    sig = torch.cat([O.make_planted_signals(d, 1, n, 150, seed=12), O.make_noise_signals(1, n, seed=13)], dim=0)
+    tr = O.greedy_pursuit(sig, d, s, want_margin=True)
+    plan = mpb.Plan(k, a, n, b, mode="gram", device=DEV).set_dictionary(d).set_refresh_every(refresh)
+    assert plan.mode == "gram" and plan.info.gram_bytes == k * k * 2 * a * 4
+    atom, pos, val, res = plan.sparse_code(sig.to(DEV), s)
+    checked = compare_with_oracle_trace(tr, atom.cpu().numpy(), pos.cpu().numpy(), val.cpu().numpy(),
+                                        res.cpu().numpy())
+    assert checked >= 100
+    assert int((tr.pos + a > n).sum()) > 0      # the case does contain truncated winners
+
+
+def test_auto_mode_resolution():
+    assert mpb.Plan(512, 1024, 2 ** 15, 64, device=DEV).mode == "gram"          # BASELINE configs[1]
+    assert mpb.Plan(512, 512, 2 ** 15, 1, device=DEV).mode == "recorrelate"      # table build not amortised
+    assert mpb.Plan(4096, 2048, 2 ** 15, 8, device=DEV).mode == "recorrelate"    # 275 GB table
 
 
 def test_config1_full_size():
