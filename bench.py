@@ -44,6 +44,7 @@ WORKLOADS = {
            "atom-sharded with a per-step NCCL all-gather of 16-byte records"),
 }
 METRIC = "MP atoms/sec (4096x2048 dict, 2^15 sig)"
+METRIC_BY_WORKLOAD = {"c2": "MP atoms/sec (512x1024 dict, 2^15 sig)", "c1": "MP atoms/sec (512x512 dict, 2^15 sig)"}
 UNIT = "atoms/s"
 
 
@@ -405,7 +406,19 @@ def main():
     alg_bytes = 8 * ((k + 1) // 2) * m_fft + 8 * batch * m_fft + 8 * batch * k * nvb + 4 * batch * k * nb \
         + 8 * batch * k
     roofline = None
-    if corr_n:
+    gram_ms, gram_n = kernel_times["gram_update"]
+    if plan.mode == "gram" and gram_n:
+        # dominant kernel in GRAM mode: k_gram_update.  Algorithmic bytes per launch:
+        # per signal 4*K*W (Gram row read) + 8*K*W (map window read-modify-write), W = 2A-1.
+        w = 2 * a - 1
+        gram_bytes = 12 * k * w * batch
+        per_launch_s = gram_ms / gram_n / 1e3
+        achieved = gram_bytes / per_launch_s / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_gram_update (map window -= v * Gram row, fused block/row maxima)",
+                    "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "peak_source": peak_src, "traffic": None, "alg_bytes_per_launch": gram_bytes,
+                    "ms_per_launch": gram_ms / gram_n, "share_of_step": gram_ms / ms_total}
+    elif corr_n:
         per_launch_s = corr_ms / corr_n / 1e3
         achieved = alg_bytes / per_launch_s / 1e9
         flops = batch * ((k + 1) // 2) * 5.0 * m_fft * (m_fft.bit_length() - 1)   # 5 M log2 M per complex IFFT
@@ -420,18 +433,19 @@ def main():
                              "achieved_tflops": flops / per_launch_s / 1e12,
                              "nominal_peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12}}
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC_BY_WORKLOAD.get(args.workload, METRIC), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic (planted atoms + noise, seeded; dictionary U(-1,1) unit-normed)",
         "config": {"workload": desc if standard else f"NON-STANDARD batch={batch} iterations={s} of: {desc}",
                    "batch_per_gpu": batch, "n_samples": n, "n_atoms": k, "atom_size": a, "iterations": s,
                    "mode": plan.mode, "fft_size": m_fft, "block": blk,
                    "parallelism": f"batch-sharded x{world}, no collective",
-                   "l2": "inputs larger than L2 (signals 128 MiB + pair spectra 128 MiB + block-max table 4 GiB "
-                         "per pass)" if standard else "working set as configured"},
+                   "l2": f"inputs larger than L2: plan working set {int(plan.device_bytes) >> 20} MiB + signals "
+                         f"{batch * n * 4 >> 20} MiB"},
         "gpu_launches": int(launches), "clocks": clocks,
         "kernel_ms": {"first_pass": first_ms / max(first_n, 1), "apply_per_iteration": apply_ms / max(apply_n, 1),
-                      "recorrelate_per_iteration": corr_ms / max(corr_n, 1)},
+                      "recorrelate_per_iteration": corr_ms / max(corr_n, 1),
+                      "gram_update_per_iteration": gram_ms / max(gram_n, 1)},
         "setup": {"dictionary_tables_ms": dict_ms, "inputs_and_plan_s": setup_s,
                   "plan_device_bytes": int(plan.device_bytes)},
     }

@@ -87,8 +87,9 @@ int mpb200_plan_set_option(mpb200_plan_t plan, int option, long long value);
  * event on `stream` after the first full pass and after every apply and
  * re-correlation launch.  mpb200_plan_timing_read waits for the last event and
  * returns, for tag 1 = first pass, 2 = select+subtract+window FFT ("apply"),
- * 3 = window re-correlation + block/row maxima, the accumulated milliseconds
- * and number of intervals since the previous read (arrays of 4; index 0 unused). */
+ * 3 = window re-correlation + block/row maxima, 4 = Gram-table map update
+ * (GRAM mode), the accumulated milliseconds and number of intervals since the
+ * previous read (arrays of 5; index 0 unused). */
 int mpb200_plan_timing_enable(mpb200_plan_t plan, int enable);
 int mpb200_plan_timing_read(mpb200_plan_t plan, double* ms_by_tag, int64_t* count_by_tag);
 

@@ -521,46 +521,106 @@ struct GramArgs {
     int nloc, N, NB, blk_shift, A, GS;
 };
 
+// The window is walked in chunks of 128 positions (one float4 of the map per lane; the chunk
+// start is a multiple of BLK or of 128, so the map accesses are 16-byte aligned, while the Gram
+// row is read with scalar loads because its offset t - p + A - 1 has arbitrary alignment).
+// BLK >= 128: a block is BLK/128 chunks, reduced over the whole warp; BLK < 128: a chunk holds
+// 128/BLK blocks, reduced over segments of BLK/4 lanes.  Lane i ends up holding refreshed block i.
+template <int BLK>
 __global__ void __launch_bounds__(256)
 k_gram_update(const GramArgs a) {
+    static_assert(BLK >= 16 && BLK <= 256, "block size");
+    constexpr int LPB = BLK >= 128 ? 32 : BLK / 4;         // lanes that share a block inside a chunk
+    constexpr int CPB = BLK >= 128 ? BLK / 128 : 1;        // chunks per block
+    constexpr int BPC = BLK >= 128 ? 1 : 128 / BLK;        // blocks per chunk
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= a.rows) return;
     const int b = row / a.nloc, j = row - b * a.nloc;
     const GramUpdate u = a.upd[b];
     if (!u.valid) return;
-    const int p = u.position, blk = 1 << a.blk_shift;
+    const int p = u.position;
     const float nv = -u.value;
     const int first = max(0, p - a.A + 1), last = min(a.N - 1, p + a.A - 1);
-    const int blk0 = first >> a.blk_shift, nvb = (last >> a.blk_shift) - blk0 + 1;   // nvb <= 32
+    const int blk0 = first / BLK, nvb = last / BLK - blk0 + 1;   // nvb <= 32
     const float* __restrict__ g = a.gram + ((size_t)u.atom * a.nloc + j) * a.GS + (a.A - 1 - p);   // g[t]
     float* __restrict__ m = a.map + (size_t)row * a.N;
     const size_t bm0 = (size_t)row * a.NB;
+    const bool vec_ok = (a.N % 4 == 0);
     float my_v = -INFINITY;
     int my_p = INT_MAX;
-    for (int i = 0; i < nvb; ++i) {
-        const int tb = (blk0 + i) << a.blk_shift;
+    float carry_v = -INFINITY;   // BLK > 128: maximum of the block's earlier chunks
+    int carry_p = INT_MAX;
+    const int c0 = (blk0 * BLK) / 128 * 128;                  // first chunk start (multiple of 128, <= blk0*BLK)
+    const int c_end = (blk0 + nvb) * BLK;
+    for (int tc = c0; tc < c_end; tc += 128) {
+        const int t = tc + 4 * lane;
+        float x[4];
+        if (vec_ok && t + 3 < a.N) {
+            const float4 q = *reinterpret_cast<const float4*>(m + t);
+            x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = (t + e < a.N) ? m[t + e] : -INFINITY;
+        }
+        bool touched = false;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int tt = t + e;
+            if (tt >= first && tt <= last) {
+                x[e] = fmaf(nv, __ldg(g + tt), x[e]);
+                touched = true;
+            }
+        }
+        if (touched) {
+            if (vec_ok && t + 3 < a.N) {
+                *reinterpret_cast<float4*>(m + t) = make_float4(x[0], x[1], x[2], x[3]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (t + e < a.N) m[t + e] = x[e];
+            }
+        }
         float best = -INFINITY;
         int at = INT_MAX;
-        for (int t = tb + lane; t < tb + blk && t < a.N; t += 32) {
-            float x = m[t];
-            if (t >= first && t <= last) {
-                x = fmaf(nv, __ldg(g + t), x);
-                m[t] = x;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (x[e] > best) {
+                best = x[e];
+                at = t + e;
             }
-            if (x > best) {
-                best = x;
-                at = t;
+#pragma unroll
+        for (int off = LPB / 2; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, at, off);
+            take_better(best, at, ov, oi);
+        }
+        if constexpr (CPB > 1) {
+            take_better(best, at, carry_v, carry_p);          // earlier chunk: lower positions win ties
+            const bool block_done = ((tc + 128) % BLK) == 0;
+            carry_v = block_done ? -INFINITY : best;
+            carry_p = block_done ? INT_MAX : at;
+            if (!block_done) continue;
+        }
+        // every lane of a segment now holds its block's (max, argmax); hand block (blk0 + lane) to `lane`
+        const int first_blk = (BLK >= 128) ? tc / BLK : tc / BLK;            // first block of this chunk
+        const int want = blk0 + lane;                                          // block this lane keeps
+        const int rel = want - first_blk;
+        const bool mine = rel >= 0 && rel < BPC && lane < nvb;
+        const int src = mine ? rel * LPB : 0;
+        const float sv = __shfl_sync(0xffffffffu, best, src);
+        const int sp = __shfl_sync(0xffffffffu, at, src);
+        if (mine) {
+            my_v = sv;
+            my_p = sp;
+        }
+        // segment leaders publish their block
+        if ((lane % LPB) == 0) {
+            const int bi = first_blk + lane / LPB;
+            if (bi >= blk0 && bi < blk0 + nvb) {
+                a.bm_val[bm0 + bi] = best;
+                a.bm_pos[bm0 + bi] = at;
             }
-        }
-        warp_argmax(best, at);
-        if (lane == i) {
-            my_v = best;
-            my_p = at;
-        }
-        if (lane == 0) {
-            a.bm_val[bm0 + blk0 + i] = best;
-            a.bm_pos[bm0 + blk0 + i] = at;
         }
     }
     // row maximum over all NB blocks: refreshed ones from registers, the rest from the table

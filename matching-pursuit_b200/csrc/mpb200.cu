@@ -240,6 +240,18 @@ static int launch_apply(Plan* p, int batch, const Best* winner, int step, int n_
     return MPB200_OK;
 }
 
+// timing marker: everything enqueued on `st` since the previous marker is attributed to `tag`
+static void mark(Plan* p, int tag, cudaStream_t st) {
+    if (!p->timing) return;
+    if (p->ev_used == p->ev_pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return; }
+        p->ev_pool.push_back((void*)e);
+    }
+    cudaEventRecord((cudaEvent_t)p->ev_pool[p->ev_used++], st);
+    p->ev_tag.push_back(tag);
+}
+
 // Refresh the map / block maxima / row maxima after k_apply's subtraction.
 static int step_refresh(Plan* p, int batch, cudaStream_t st) {
     int rc = MPB200_OK;
@@ -265,8 +277,16 @@ static int step_refresh(Plan* p, int batch, cudaStream_t st) {
             g.blk_shift = p->blk_shift;
             g.A = p->A;
             g.GS = p->GS;
-            k_gram_update<<<(g.rows + 7) / 8, 256, 0, st>>>(g);
+            switch (p->blk) {
+                case 16: k_gram_update<16><<<(g.rows + 7) / 8, 256, 0, st>>>(g); break;
+                case 32: k_gram_update<32><<<(g.rows + 7) / 8, 256, 0, st>>>(g); break;
+                case 64: k_gram_update<64><<<(g.rows + 7) / 8, 256, 0, st>>>(g); break;
+                case 128: k_gram_update<128><<<(g.rows + 7) / 8, 256, 0, st>>>(g); break;
+                case 256: k_gram_update<256><<<(g.rows + 7) / 8, 256, 0, st>>>(g); break;
+                default: return fail(MPB200_EINVAL, "unsupported block size");
+            }
             MPB_LAUNCH_CHECK("k_gram_update");
+            mark(p, 4, st);
             // winners truncated at the right edge: FFT re-correlation of their windows, written into the map
             CorrArgs a = base_corr_args(p);
             a.win = p->win_step;
@@ -320,18 +340,6 @@ static int build_pair_spectra(Plan* p, cudaStream_t st) {
     });
     MPB_LAUNCH_CHECK("k_pair_spectra");
     return MPB200_OK;
-}
-
-// timing marker: everything enqueued on `st` since the previous marker is attributed to `tag`
-static void mark(Plan* p, int tag, cudaStream_t st) {
-    if (!p->timing) return;
-    if (p->ev_used == p->ev_pool.size()) {
-        cudaEvent_t e;
-        if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return; }
-        p->ev_pool.push_back((void*)e);
-    }
-    cudaEventRecord((cudaEvent_t)p->ev_pool[p->ev_used++], st);
-    p->ev_tag.push_back(tag);
 }
 
 static int check_plan(Plan* p, bool need_dict) {
@@ -525,7 +533,7 @@ int mpb200_plan_timing_enable(mpb200_plan_t plan, int enable) {
 int mpb200_plan_timing_read(mpb200_plan_t plan, double* ms_by_tag, int64_t* count_by_tag) {
     Plan* p = reinterpret_cast<Plan*>(plan);
     if (!p || !ms_by_tag || !count_by_tag) return fail(MPB200_EINVAL, "null argument");
-    for (int t = 0; t < 4; ++t) { ms_by_tag[t] = 0.0; count_by_tag[t] = 0; }
+    for (int t = 0; t < 5; ++t) { ms_by_tag[t] = 0.0; count_by_tag[t] = 0; }
     if (p->ev_used) MPB_CUDA(cudaEventSynchronize((cudaEvent_t)p->ev_pool[p->ev_used - 1]));
     for (size_t i = 1; i < p->ev_used; ++i) {
         const int tag = p->ev_tag[i];

@@ -88,12 +88,13 @@ class Plan:
         check(self._lib.mpb200_plan_timing_enable(self._h, int(bool(enable))), "mpb200_plan_timing_enable")
 
     def timing_read(self) -> dict:
-        """{'first_pass'|'apply'|'recorrelate': (milliseconds, intervals)} since the last read."""
-        ms = (C.c_double * 4)()
-        cnt = (C.c_int64 * 4)()
+        """{'first_pass'|'apply'|'recorrelate'|'gram_update': (milliseconds, intervals)} since the last read."""
+        ms = (C.c_double * 5)()
+        cnt = (C.c_int64 * 5)()
         with torch.cuda.device(self.device):
             check(self._lib.mpb200_plan_timing_read(self._h, ms, cnt), "mpb200_plan_timing_read")
-        return {"first_pass": (ms[1], cnt[1]), "apply": (ms[2], cnt[2]), "recorrelate": (ms[3], cnt[3])}
+        return {"first_pass": (ms[1], cnt[1]), "apply": (ms[2], cnt[2]), "recorrelate": (ms[3], cnt[3]),
+                "gram_update": (ms[4], cnt[4])}
 
     # ---- dictionary -----------------------------------------------------
     def set_dictionary(self, d: torch.Tensor, normalize: bool = True) -> "Plan":
