@@ -34,6 +34,7 @@ class MpbError(RuntimeError):
 
 def nvcc_command(out_path: str = LIB_PATH, extra=()):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    extra = tuple(extra) + tuple(os.environ.get("MPB_NVCC_FLAGS", "").split())
     return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
             "-Xcompiler", "-fPIC", "-shared", *extra, "-o", out_path] + [os.path.join(CSRC, s) for s in SOURCES]
 

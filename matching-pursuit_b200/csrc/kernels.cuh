@@ -176,23 +176,41 @@ struct CorrArgs {
     int* bm_pos;
     float* row_val;
     int* row_pos;
+    int bm_cap;      // ROWMAX kernels: capacity (in positions) of the separate output staging buffer
     float* dense;
     long long dense_row_stride;   // between windows' source rows
     long long dense_atom_stride;  // between atoms
     int dense_col_off;            // column = t0 + m + dense_col_off
 };
 
+// Shared memory: [tw2: 256 complex][per transform: FFT buffer SMEM_CPX complex][per transform, only
+// when ROWMAX: a separate block-max staging buffer of bm_cap float2 + 64 (value, position) slots].
+// The separate staging buffer lets the step kernel drop two of its CTA barriers per window (the
+// FFT buffer is not reused for the outputs, so nothing has to wait for pass 3 to drain or for the
+// block-max readers to finish before the next window's pass 1 stores).
+#ifndef MPB_CORR_MINB
+#define MPB_CORR_MINB 2      // CTAs per SM the register allocation of k_corr aims at
+#endif
+#ifndef MPB_CORR_SEP
+#define MPB_CORR_SEP 1       // 1: step kernels stage their outputs in a separate shared buffer
+#endif
 template <int M, int MODE>
-__global__ void __launch_bounds__((BlockFft<M, float>::T < 256 ? 256 : BlockFft<M, float>::T), 2)
+__global__ void __launch_bounds__((BlockFft<M, float>::T < 256 ? 256 : BlockFft<M, float>::T), MPB_CORR_MINB)
 k_corr(const CorrArgs a) {
     using F = BlockFft<M, float>;
     constexpr int TPB = F::T < 256 ? 256 : F::T;
     constexpr int NT = TPB / F::T;   // transforms (atom pairs) per CTA
     constexpr int NW = F::T / 32;    // warps per transform
+    constexpr bool SEP = MPB_CORR_SEP && (MODE & MODE_ROWMAX) != 0;
     extern __shared__ __align__(16) unsigned char smraw[];
     C32* stw2 = reinterpret_cast<C32*>(smraw);
     const int sb = threadIdx.x / F::T, tl = threadIdx.x % F::T;
     C32* sm = stw2 + 256 + (size_t)sb * F::SMEM_CPX;
+    // staging of the outputs as (atom 2q, atom 2q+1) pairs, and of the refreshed block maxima
+    float2* sY = SEP ? reinterpret_cast<float2*>(stw2 + 256 + (size_t)NT * F::SMEM_CPX) + (size_t)sb * (a.bm_cap + 64)
+                     : reinterpret_cast<float2*>(sm);
+    __shared__ float2 s_bv_static[NT * 64];
+    float2* sBV = SEP ? sY + a.bm_cap : s_bv_static + sb * 64;   // [which*32 + i] = (value, position as int bits)
     for (int i = threadIdx.x; i < 256; i += TPB) stw2[i] = a.tw2[i];
 
     int q = blockIdx.x * NT + sb;
@@ -237,66 +255,91 @@ k_corr(const CorrArgs a) {
             }
         }
         if constexpr ((MODE & MODE_BLOCKMAX) != 0) {
-            __syncthreads();  // pass-3 loads finished: the buffer is reused as two real arrays
-            float* sA = reinterpret_cast<float*>(sm);
-            float* sB = sA + M;
+            if constexpr (!SEP) __syncthreads();  // pass-3 loads finished: the FFT buffer is reused for the outputs
+            const int stage_end = wi.nvb * blk;   // <= bm_cap when SEP
 #pragma unroll
             for (int e = 0; e < F::E; ++e) {
                 const int m = F::out_index(tl, e);
-                sA[m] = r[e].x + 0.f;  // +0: canonical zero, so ties behave like the reference's exact zeros
-                sB[m] = r[e].y + 0.f;
+                if (m < stage_end) sY[m] = make_float2(r[e].x, r[e].y);
             }
             __syncthreads();
-            if (q_ok) {
-                for (int it = warp; it < 2 * wi.nvb; it += NW) {
-                    const int which = it & 1, i = it >> 1;
-                    const int k = 2 * q + which;
-                    if (k >= a.nloc) continue;
-                    const float* s = which ? sB : sA;
-                    const int hi = min((i + 1) * blk, limit);
-                    float v = -INFINITY;
-                    int at = INT_MAX;
-                    for (int m = i * blk + lane; m < hi; m += 32) {
-                        const float c = s[m];
-                        if (c > v) {
-                            v = c;
-                            at = m;
-                        }
+            const bool second = 2 * q + 1 < a.nloc;
+            for (int i = warp; i < wi.nvb; i += NW) {
+                const int hi = min((i + 1) * blk, limit);
+                float va = -INFINITY, vb = -INFINITY;
+                int ia = INT_MAX, ib = INT_MAX;
+                for (int m = i * blk + lane; m < hi; m += 32) {
+                    const float2 c = sY[m];
+                    if (c.x > va) { va = c.x; ia = m; }
+                    if (c.y > vb) { vb = c.y; ib = m; }
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {      // the two reductions interleave
+                    const float oa = __shfl_xor_sync(0xffffffffu, va, off);
+                    const int pa = __shfl_xor_sync(0xffffffffu, ia, off);
+                    const float ob = __shfl_xor_sync(0xffffffffu, vb, off);
+                    const int pb = __shfl_xor_sync(0xffffffffu, ib, off);
+                    take_better(va, ia, oa, pa);
+                    take_better(vb, ib, ob, pb);
+                }
+                if (lane == 0 && q_ok) {
+                    const int pa = (ia == INT_MAX) ? INT_MAX : wi.t0 + ia;
+                    const int pb = (ib == INT_MAX) ? INT_MAX : wi.t0 + ib;
+                    const size_t o = ((size_t)wi.row * a.nloc + 2 * q) * a.NB + wi.blk0 + i;
+                    a.bm_val[o] = va;
+                    a.bm_pos[o] = pa;
+                    if (second) {
+                        a.bm_val[o + a.NB] = vb;
+                        a.bm_pos[o + a.NB] = pb;
                     }
-                    warp_argmax(v, at);
-                    if (lane == 0) {
-                        const size_t o = ((size_t)wi.row * a.nloc + k) * a.NB + wi.blk0 + i;
-                        a.bm_val[o] = v;
-                        a.bm_pos[o] = (at == INT_MAX) ? INT_MAX : wi.t0 + at;
+                    if constexpr ((MODE & MODE_ROWMAX) != 0) {
+                        sBV[i] = make_float2(va, __int_as_float(pa));
+                        sBV[32 + i] = make_float2(vb, __int_as_float(pb));
                     }
                 }
             }
             if constexpr ((MODE & MODE_ROWMAX) != 0) {
-                __syncthreads();  // this CTA's block maxima are visible to all of its threads
-                if (q_ok) {
-                    for (int which = warp; which < 2; which += NW) {
-                        const int k = 2 * q + which;
-                        if (k >= a.nloc) continue;
-                        const size_t o = ((size_t)wi.row * a.nloc + k) * a.NB;
-                        float v = -INFINITY;
-                        int at = INT_MAX;
+                __syncthreads();  // refreshed block maxima are staged in sBV
+                // warp `which` (both atoms on warp 0 when a transform has a single warp) re-derives the row
+                // maximum of atom 2q + which.  If the old row maximum sat in a block this window did not
+                // touch, it is still valid and only has to be compared with the refreshed blocks;
+                // otherwise the whole row of block maxima is rescanned.
+                for (int which = warp; which < 2; which += NW) {
+                    if (!q_ok || (which == 1 && !second)) continue;
+                    const size_t rowi = (size_t)wi.row * a.nloc + 2 * q + which;
+                    const size_t o = rowi * a.NB;
+                    const float old_v = a.row_val[rowi];
+                    const int old_p = a.row_pos[rowi];
+                    const int old_b = old_p >> a.blk_shift;
+                    const bool old_ok = old_b < wi.blk0 || old_b >= wi.blk0 + wi.nvb;
+                    float v = -INFINITY;
+                    int at = INT_MAX;      // position (positions order like (block, offset), so ties resolve alike)
+                    if (lane < wi.nvb) {
+                        const float2 c = sBV[which * 32 + lane];
+                        v = c.x;
+                        at = __float_as_int(c.y);
+                    }
+                    if (old_ok) {
+                        if (lane == 31) take_better(v, at, old_v, old_p);   // nvb <= 22 < 32: lane 31 is free
+                    } else {
                         for (int i = lane; i < a.NB; i += 32) {
+                            if (i >= wi.blk0 && i < wi.blk0 + wi.nvb) continue;
                             const float c = a.bm_val[o + i];
-                            if (c > v) {
+                            if (c > v || (c == v && a.bm_pos[o + i] < at)) {
                                 v = c;
-                                at = i;
+                                at = a.bm_pos[o + i];
                             }
                         }
-                        warp_argmax(v, at);
-                        if (lane == 0) {
-                            a.row_val[(size_t)wi.row * a.nloc + k] = v;
-                            a.row_pos[(size_t)wi.row * a.nloc + k] = (at == INT_MAX) ? 0 : a.bm_pos[o + at];
-                        }
+                    }
+                    warp_argmax(v, at);
+                    if (lane == 0) {
+                        a.row_val[rowi] = v;
+                        a.row_pos[rowi] = (at == INT_MAX) ? 0 : at;
                     }
                 }
             }
         }
-        __syncthreads();  // buffer free for the next window
+        if constexpr (!SEP) __syncthreads();  // buffer free for the next window
     }
 }
 

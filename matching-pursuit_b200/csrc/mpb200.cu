@@ -125,13 +125,15 @@ static int launch_window_fft(Plan* p, const float* src, long long row_stride, in
 template <int MODE>
 static int launch_corr(Plan* p, CorrArgs a, int groups, cudaStream_t st) {
     if (a.nwin <= 0) return MPB200_OK;
+    a.bm_cap = p->bm_cap;
     MPB_DISPATCH_M(p->M, {
         using F = BlockFft<MM, float>;
         constexpr int TPB = F::T < 256 ? 256 : F::T;
         constexpr int NT = TPB / F::T;
-        const size_t smem = (size_t)(256 + NT * F::SMEM_CPX) * sizeof(C32);
-        static bool once = false;
-        if (!once) { MPB_CUDA(allow_smem(k_corr<MM, MODE>, smem)); once = true; }
+        size_t smem = (size_t)(256 + NT * F::SMEM_CPX) * sizeof(C32);
+        if (MPB_CORR_SEP && (MODE & MODE_ROWMAX) != 0) smem += (size_t)NT * (p->bm_cap + 64) * sizeof(float2);
+        static size_t allowed = 0;
+        if (smem > allowed) { MPB_CUDA(allow_smem(k_corr<MM, MODE>, smem)); allowed = smem; }
         dim3 grid((a.npairs + NT - 1) / NT, groups);
         k_corr<MM, MODE><<<grid, TPB, smem, st>>>(a);
     });
@@ -401,6 +403,7 @@ int mpb200_plan_create(mpb200_plan_t* out, int n_atoms, int atom_size, int n_sam
     p->vfull = (M - atom_size + 1) / p->blk;
     if (p->vfull > 32) p->vfull = 32;
     p->nchunks = (p->NB + p->vfull - 1) / p->vfull;
+    p->bm_cap = ((2 * atom_size - 2) / p->blk + 2) * p->blk;   // positions a step window can refresh
 
     // Gram table: (nloc, K?) -- the table is indexed [winner atom (any of K)][owned atom][lag]
     const uint64_t gram_bytes = (uint64_t)n_atoms * p->nloc * (2ull * atom_size) * sizeof(float);

@@ -17,6 +17,7 @@ struct Plan {
     int M = 0, blk = 0, blk_shift = 0, NB = 0;      // window FFT size, block-max granularity
     int vfull = 0, nchunks = 0;                     // full pass: blocks per window, windows per signal
     int wcap = 0;                                   // window-spectrum slots
+    int bm_cap = 0;                                 // positions refreshed by one step window (staging size)
     int cur_batch = 0;                              // batch loaded by mpb200_begin (0 = none)
     bool dict_set = false;
 
