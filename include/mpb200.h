@@ -33,10 +33,15 @@ extern "C" {
 #define MPB200_ESTATE (-4)   /* call sequence error (no dictionary set, ...) */
 
 /* How the correlation map is kept up to date after the first full pass. */
-#define MPB200_MODE_AUTO 0        /* GRAM when the table fits the budget, else RECORRELATE */
+#define MPB200_MODE_AUTO 0        /* GRAM when the table fits and is amortised, else SGRAM when the map of a useful
+                                     sub-batch fits, else RECORRELATE */
 #define MPB200_MODE_RECORRELATE 1 /* re-correlate the +-A window of each winner by FFT; only block maxima are resident */
 #define MPB200_MODE_GRAM 2        /* resident map, updated from a precomputed atom cross-correlation table */
 #define MPB200_MODE_FULL 3        /* recompute the whole map every step (the reference's schedule) */
+#define MPB200_MODE_SGRAM 4       /* resident map, updated from Gram rows that are SYNTHESISED per step from cached
+                                     atom spectra (one inverse FFT of >= 2A points per atom pair); the K^2(2A-1)
+                                     table is never stored.  Batches larger than the resident capacity are
+                                     processed in sub-batches. */
 
 typedef struct mpb200_plan* mpb200_plan_t;
 
@@ -47,7 +52,8 @@ typedef struct mpb200_plan_info {
     int32_t block;           /* positions per block-max entry */
     int32_t n_blocks;        /* ceil(n_samples / block) */
     int32_t atom_lo, atom_hi;/* atoms owned by this plan (atom sharding) */
-    int32_t reserved0, reserved1;
+    int32_t resident_batch;  /* signals processed at once (sub-batch size of the map modes) */
+    int32_t fft_size2;       /* SGRAM: transform length of the synthesised Gram rows */
     uint64_t device_bytes;   /* device memory owned by the plan */
     uint64_t gram_bytes;     /* of which: Gram table */
 } mpb200_plan_info;
@@ -69,14 +75,17 @@ unsigned long long mpb200_launch_count(void);
 /* Plan: sizes workspaces for signals of n_samples, batches up to max_batch and
  * a dictionary of n_atoms x atom_size of which this plan owns atoms
  * [atom_lo, atom_hi) (pass 0, n_atoms for no sharding).  gram_budget_bytes
- * bounds the Gram table in AUTO mode (0 = default 40% of free memory).
+ * bounds the Gram table in AUTO mode (0 = default 40% of free memory); in
+ * SGRAM mode it bounds the resident correlation map instead (0 = 85% of free
+ * memory), which sets plan_info.resident_batch: larger batches are processed
+ * in balanced sub-batches of at most that many signals.
  * No reference counterpart: the reference re-derives everything per call
  * (modules/matchingpursuit.py:254-259). */
 int mpb200_plan_create(mpb200_plan_t* plan, int n_atoms, int atom_size, int n_samples, int max_batch,
                        int mode, int atom_lo, int atom_hi, uint64_t gram_budget_bytes);
 int mpb200_plan_destroy(mpb200_plan_t plan);
 int mpb200_plan_info_get(mpb200_plan_t plan, mpb200_plan_info* info);
-/* Options.  MPB200_OPT_REFRESH_EVERY (GRAM mode): re-correlate the whole map from
+/* Options.  MPB200_OPT_REFRESH_EVERY (GRAM and SGRAM modes): re-correlate the whole map from
  * the residual every `value` iterations to bound the drift of the incremental
  * fp32 updates (0 = never, the default). */
 #define MPB200_OPT_REFRESH_EVERY 1
@@ -88,7 +97,7 @@ int mpb200_plan_set_option(mpb200_plan_t plan, int option, long long value);
  * re-correlation launch.  mpb200_plan_timing_read waits for the last event and
  * returns, for tag 1 = first pass, 2 = select+subtract+window FFT ("apply"),
  * 3 = window re-correlation + block/row maxima, 4 = Gram-table map update
- * (GRAM mode), the accumulated milliseconds and number of intervals since the
+ * (GRAM mode) / synthesised Gram-row map update (SGRAM mode), the accumulated milliseconds and number of intervals since the
  * previous read (arrays of 5; index 0 unused). */
 int mpb200_plan_timing_enable(mpb200_plan_t plan, int enable);
 int mpb200_plan_timing_read(mpb200_plan_t plan, double* ms_by_tag, int64_t* count_by_tag);

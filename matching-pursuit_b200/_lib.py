@@ -17,15 +17,16 @@ LIB_PATH = os.path.join(HERE, "libmpb200.so")
 SOURCES = ["mpb200.cu", "fftconv.cu"]
 HEADERS = ["kernels.cuh", "fft_core.cuh", "bigfft.cuh", "types.h", "plan.h"]
 
-MODE_AUTO, MODE_RECORRELATE, MODE_GRAM, MODE_FULL = 0, 1, 2, 3
-MODES = {"auto": MODE_AUTO, "recorrelate": MODE_RECORRELATE, "gram": MODE_GRAM, "full": MODE_FULL}
+MODE_AUTO, MODE_RECORRELATE, MODE_GRAM, MODE_FULL, MODE_SGRAM = 0, 1, 2, 3, 4
+MODES = {"auto": MODE_AUTO, "recorrelate": MODE_RECORRELATE, "gram": MODE_GRAM, "full": MODE_FULL,
+         "sgram": MODE_SGRAM}
 MODE_NAMES = {v: k for k, v in MODES.items()}
 
 
 class PlanInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "n_atoms", "atom_size", "n_samples", "max_batch", "mode", "fft_size", "block", "n_blocks",
-        "atom_lo", "atom_hi", "reserved0", "reserved1")] + [("device_bytes", C.c_uint64), ("gram_bytes", C.c_uint64)]
+        "atom_lo", "atom_hi", "resident_batch", "fft_size2")] + [("device_bytes", C.c_uint64), ("gram_bytes", C.c_uint64)]
 
 
 class MpbError(RuntimeError):

@@ -189,10 +189,10 @@ struct CorrArgs {
 // FFT buffer is not reused for the outputs, so nothing has to wait for pass 3 to drain or for the
 // block-max readers to finish before the next window's pass 1 stores).
 #ifndef MPB_CORR_MINB
-#define MPB_CORR_MINB 2      // CTAs per SM the register allocation of k_corr aims at
+#define MPB_CORR_MINB 3      // CTAs per SM the register allocation of k_corr aims at (80 registers, 8 B spilled)
 #endif
 #ifndef MPB_CORR_SEP
-#define MPB_CORR_SEP 1       // 1: step kernels stage their outputs in a separate shared buffer
+#define MPB_CORR_SEP 0       // 1: step kernels stage their outputs in a separate shared buffer (costs the 3rd CTA)
 #endif
 template <int M, int MODE>
 __global__ void __launch_bounds__((BlockFft<M, float>::T < 256 ? 256 : BlockFft<M, float>::T), MPB_CORR_MINB)
@@ -689,6 +689,257 @@ k_gram_update(const GramArgs a) {
         a.row_val[row] = v;
         a.row_pos[row] = (bi_best == INT_MAX) ? 0 : (fresh ? fp : a.bm_pos[bm0 + bi_best]);
     }
+}
+
+// ---------------------------------------------------------------------------
+// Asynchronous bulk copies (TMA, 1-D form) and the mbarrier that tracks them.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gmem_dst, const void* smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Order-preserving map float -> int (for redux.sync max); -0 is folded into +0 first.
+__device__ __forceinline__ int float_key(float v) {
+    int k = __float_as_int(v + 0.0f);
+    return k ^ ((k >> 31) & 0x7fffffff);
+}
+// Warp (max, lowest position of the max): two redux.sync instead of a shuffle tree.
+__device__ __forceinline__ void warp_argmax_redux(float& v, int& at) {
+    const int key = float_key(v);
+    const int kmax = __reduce_max_sync(0xffffffffu, key);
+    at = __reduce_min_sync(0xffffffffu, key == kmax ? at : INT_MAX);
+    v = __int_as_float(kmax ^ ((kmax >> 31) & 0x7fffffff));
+}
+
+// ---------------------------------------------------------------------------
+// SPECTRAL-GRAM mode update ("the Gram row is synthesised, not stored").  For signal b with winner
+// (k*, p, v) and atom pair q the cross-correlations
+//     G[k*, 2q, l] + i G[k*, 2q+1, l] = IFFT_M2( atomspec[k*] * pairspec2[q] )[l + A - 1],   |l| < A
+// come out of ONE inverse transform of M2 >= 2A points -- half the length the windowed
+// re-correlation needs, and every output is used -- and are applied to the resident map rows
+//     map[b, 2q(+1), t] -= v * G[k*, 2q(+1), t - p]          (fused multiply-add)
+// followed by the block maxima of the touched blocks and the row maxima, as in k_corr.
+//
+// The map window (whole blocks: <= bm_cap positions of both rows) is STAGED in shared memory by
+// bulk asynchronous copies: the loads are issued before the transform and land while it runs, the
+// update is a conflict-free shared-memory read-modify-write straight from the FFT registers
+// (thread tl owns outputs tl + T*u + (M2/16)*m3, i.e. consecutive lanes touch consecutive
+// positions), and the rows go back with bulk stores that overlap the block-max phase and the next
+// signal's transform.  No register ever waits on HBM.
+//
+// grid = (ceil(pairs / NT), signal groups); a CTA keeps its pair(s) and walks signals
+// b = blockIdx.y, blockIdx.y + gridDim.y, ...
+// ---------------------------------------------------------------------------
+struct DeltaArgs {
+    const C32* atomspec;    // (K, M2): forward spectrum of [0^(A-1), d_k]
+    const C32* pairspec2;   // (npairs, M2): inverse-kernel spectrum of d[2q] + i d[2q+1], scaled 1/M2
+    const GramUpdate* upd;  // (B)
+    int batch, npairs, nloc;
+    float* map;             // (B, nloc, NS)
+    int N, NS, NB, blk_shift, A;
+    int cap;                // staged positions per row (bm_cap: whole blocks covering any +-A window)
+    const C32* tw1;         // BlockFft<M2> tables
+    const C32* tw2;
+    float* bm_val;
+    int* bm_pos;
+    float* row_val;
+    int* row_pos;
+};
+
+#ifndef MPB_DELTA_MINB
+#define MPB_DELTA_MINB 3
+#endif
+template <int M2>
+__global__ void __launch_bounds__((BlockFft<M2, float>::T < 256 ? 256 : BlockFft<M2, float>::T), MPB_DELTA_MINB)
+k_delta(const DeltaArgs a) {
+    using F = BlockFft<M2, float>;
+    constexpr int TPB = F::T < 256 ? 256 : F::T;
+    constexpr int NT = TPB / F::T;
+    constexpr int NW = F::T / 32;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    C32* stw2 = reinterpret_cast<C32*>(smraw);
+    const int sb = threadIdx.x / F::T, tl = threadIdx.x % F::T;
+    C32* sm = stw2 + 256 + (size_t)sb * F::SMEM_CPX;
+    float* st0 = reinterpret_cast<float*>(stw2 + 256 + (size_t)NT * F::SMEM_CPX) + (size_t)sb * 2 * a.cap;
+    float* st1 = st0 + a.cap;
+    __shared__ float2 s_bv_static[NT * 64];
+    __shared__ __align__(8) unsigned long long s_bar[NT];
+    float2* sBV = s_bv_static + sb * 64;                 // [which*32 + block] = (value, position as int bits)
+    unsigned long long* bar = s_bar + sb;
+    for (int i = threadIdx.x; i < 256; i += TPB) stw2[i] = a.tw2[i];
+    if (tl == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+    }
+
+    int q = blockIdx.x * NT + sb;
+    const bool q_ok = q < a.npairs;
+    if (!q_ok) q = a.npairs - 1;
+    const C32* __restrict__ Eq = a.pairspec2 + (size_t)q * M2;
+    const bool second = 2 * q + 1 < a.nloc;
+    const int blk = 1 << a.blk_shift;
+    const int warp = tl >> 5, lane = tl & 31;
+    unsigned phase = 0;
+    __syncthreads();
+
+    for (int b = blockIdx.y; b < a.batch; b += gridDim.y) {
+        const GramUpdate u = a.upd[b];
+        if (!u.valid) continue;                          // CTA-uniform: this signal takes the FFT route
+        const int p = u.position;
+        const float nv = -u.value;
+        const int first = max(0, p - a.A + 1), last = p + a.A - 1;     // valid => p + A <= N
+        const int blk0 = first >> a.blk_shift, nvb = (last >> a.blk_shift) - blk0 + 1;
+        const int start = blk0 << a.blk_shift;
+        const int cnt = min(nvb << a.blk_shift, a.NS - start);          // staged floats per row (multiple of 4)
+        float* __restrict__ m0 = a.map + ((size_t)b * a.nloc + 2 * q) * a.NS + start;
+        float* __restrict__ m1 = m0 + a.NS;
+        if (tl == 0 && q_ok) {
+            bulk_wait_read0();                           // the previous signal's stores have left the staging rows
+            const unsigned bytes = (unsigned)cnt * 4u;
+            mbar_expect_tx(bar, second ? 2u * bytes : bytes);
+            bulk_load(st0, m0, bytes, bar);
+            if (second) bulk_load(st1, m1, bytes, bar);
+        }
+        const C32* __restrict__ S = a.atomspec + (size_t)u.atom * M2;
+        C32 r[F::E];
+#pragma unroll
+        for (int e = 0; e < F::E; ++e) {
+            const int j = F::in_index(tl, e);
+            const float2 ev = __ldg(reinterpret_cast<const float2*>(Eq + j));
+            const float2 sv = __ldg(reinterpret_cast<const float2*>(S + j));
+            r[e] = cmul(C32{sv.x, sv.y}, C32{ev.x, ev.y});
+        }
+        F::template pass1<1>(r, tl, sm, a.tw1);
+        __syncthreads();
+        F::template pass2<1>(r, tl, sm, stw2);
+        __syncthreads();
+        F::template pass3<1>(r, tl, sm);
+
+        if (q_ok) {
+            while (!mbar_try_wait(bar, phase)) {}
+            phase ^= 1u;
+            // output m is lag m - (A-1), i.e. position t = p - (A-1) + m, staged at index t - start
+            const int off = p - (a.A - 1) - start;
+            const int mmax = 2 * a.A - 1;
+#pragma unroll
+            for (int e = 0; e < F::E; ++e) {
+                const int m = F::out_index(tl, e);
+                const int i = m + off;
+                if (m < mmax && i >= 0) {
+                    st0[i] = fmaf(nv, r[e].x, st0[i]);
+                    if (second) st1[i] = fmaf(nv, r[e].y, st1[i]);
+                }
+            }
+            fence_proxy_async();                         // generic-proxy writes -> visible to the bulk stores
+        }
+        __syncthreads();                                 // rows updated; FFT buffer free
+        if (tl == 0 && q_ok) {
+            bulk_store(m0, st0, (unsigned)cnt * 4u);
+            if (second) bulk_store(m1, st1, (unsigned)cnt * 4u);
+            bulk_commit();
+        }
+        if (q_ok) {
+            const int ntask = second ? 2 * nvb : nvb;
+            for (int task = warp; task < ntask; task += NW) {
+                const int which = task >= nvb ? 1 : 0;
+                const int i = task - which * nvb;
+                const float* __restrict__ row = (which ? st1 : st0) + (i << a.blk_shift);
+                const int t0 = start + (i << a.blk_shift);
+                const int lim = a.N - t0;                // positions j >= lim are beyond the signal
+                float v = -INFINITY;
+                int at = INT_MAX;
+                if (blk >= 128) {
+                    for (int j = 4 * lane; j < blk; j += 128) {
+                        const float4 c = *reinterpret_cast<const float4*>(row + j);
+                        if (j + 3 < lim) {
+                            if (c.x > v) { v = c.x; at = j; }
+                            if (c.y > v) { v = c.y; at = j + 1; }
+                            if (c.z > v) { v = c.z; at = j + 2; }
+                            if (c.w > v) { v = c.w; at = j + 3; }
+                        } else {
+                            if (j < lim && c.x > v) { v = c.x; at = j; }
+                            if (j + 1 < lim && c.y > v) { v = c.y; at = j + 1; }
+                            if (j + 2 < lim && c.z > v) { v = c.z; at = j + 2; }
+                        }
+                    }
+                } else {
+                    for (int j = lane; j < blk; j += 32) {
+                        const float c = row[j];
+                        if (j < lim && c > v) { v = c; at = j; }
+                    }
+                }
+                warp_argmax_redux(v, at);
+                if (lane == 0) {
+                    const int pos = (at == INT_MAX) ? INT_MAX : t0 + at;
+                    const size_t o = ((size_t)b * a.nloc + 2 * q + which) * a.NB + blk0 + i;
+                    a.bm_val[o] = v;
+                    a.bm_pos[o] = pos;
+                    sBV[which * 32 + i] = make_float2(v, __int_as_float(pos));
+                }
+            }
+        }
+        __syncthreads();   // block maxima staged; nobody reads the staging rows any more
+        for (int which = warp; which < 2; which += NW) {
+            if (!q_ok || (which == 1 && !second)) continue;
+            const size_t rowi = (size_t)b * a.nloc + 2 * q + which;
+            const size_t o = rowi * a.NB;
+            float v = -INFINITY;
+            int at = INT_MAX;
+            if (lane < nvb) {
+                const float2 c = sBV[which * 32 + lane];
+                v = c.x;
+                at = __float_as_int(c.y);
+            }
+            const float old_v = a.row_val[rowi];
+            const int old_p = a.row_pos[rowi];
+            const int old_b = old_p >> a.blk_shift;
+            const bool old_ok = old_b < blk0 || old_b >= blk0 + nvb;
+            if (old_ok) {
+                if (lane == 31) take_better(v, at, old_v, old_p);       // nvb <= 30: lane 31 is free
+            } else {
+                for (int i = lane; i < a.NB; i += 32) {
+                    if (i >= blk0 && i < blk0 + nvb) continue;
+                    const float c = a.bm_val[o + i];
+                    const int cp = a.bm_pos[o + i];
+                    if (c > v || (c == v && cp < at)) {
+                        v = c;
+                        at = cp;
+                    }
+                }
+            }
+            warp_argmax(v, at);
+            if (lane == 0) {
+                a.row_val[rowi] = v;
+                a.row_pos[rowi] = (at == INT_MAX) ? 0 : at;
+            }
+        }
+        // the next signal's bulk loads are issued by tl == 0 (warp 0), which has passed the row phase
+        // itself; warps running ahead only touch the FFT buffer until the next barrier.
+    }
+    if (tl == 0 && q_ok) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
 }
 
 // ---------------------------------------------------------------------------

@@ -108,18 +108,23 @@ static void free_plan(Plan* p) {
 // ---------------------------------------------------------------------------
 // launches
 // ---------------------------------------------------------------------------
-static int launch_window_fft(Plan* p, const float* src, long long row_stride, int row_len, const Win* win, int nwin,
-                             C32* winspec, cudaStream_t st) {
+static int launch_window_fft_ex(int M, const C32* tw1, const C32* tw2, const float* src, long long row_stride,
+                                int row_len, const Win* win, int nwin, C32* winspec, cudaStream_t st) {
     if (nwin <= 0) return MPB200_OK;
-    MPB_DISPATCH_M(p->M, {
+    MPB_DISPATCH_M(M, {
         using F = BlockFft<MM, float>;
         const size_t smem = (size_t)(F::SMEM_CPX + 256) * sizeof(C32);
         static bool once = false;
         if (!once) { MPB_CUDA(allow_smem(k_window_fft<MM>, smem)); once = true; }
-        k_window_fft<MM><<<nwin, F::T, smem, st>>>(src, row_stride, row_len, win, p->tw1, p->tw2, winspec);
+        k_window_fft<MM><<<nwin, F::T, smem, st>>>(src, row_stride, row_len, win, tw1, tw2, winspec);
     });
     MPB_LAUNCH_CHECK("k_window_fft");
     return MPB200_OK;
+}
+
+static int launch_window_fft(Plan* p, const float* src, long long row_stride, int row_len, const Win* win, int nwin,
+                             C32* winspec, cudaStream_t st) {
+    return launch_window_fft_ex(p->M, p->tw1, p->tw2, src, row_stride, row_len, win, nwin, winspec, st);
 }
 
 template <int MODE>
@@ -182,9 +187,10 @@ static int full_pass(Plan* p, int batch, float* dense, cudaStream_t st, bool wit
         a.win = p->win_full + w0;
         a.nwin = n;
         if (dense) {
+            const long long rs = (dense == p->map) ? p->NS : p->N;     // the resident map may have padded rows
             a.dense = dense;
-            a.dense_row_stride = (long long)p->nloc * p->N;
-            a.dense_atom_stride = p->N;
+            a.dense_row_stride = (long long)p->nloc * rs;
+            a.dense_atom_stride = rs;
             a.dense_col_off = 0;
             if (with_maxima) rc = launch_corr<MODE_DENSE | MODE_BLOCKMAX>(p, a, corr_groups(p, n), st);
             else rc = launch_corr<MODE_DENSE>(p, a, corr_groups(p, n), st);
@@ -227,7 +233,7 @@ static int launch_apply(Plan* p, int batch, const Best* winner, int step, int n_
     a.tw2 = p->tw2;
     a.winspec = p->winspec;
     a.do_fft = do_fft;
-    a.gram = p->mode == MPB200_MODE_GRAM;
+    a.gram = p->mode == MPB200_MODE_GRAM || p->mode == MPB200_MODE_SGRAM;
     a.upd = p->upd;
     a.trunc_count = p->trunc_count;
     a.parity = (int)(p->iter & 1u);
@@ -259,6 +265,57 @@ static int step_refresh(Plan* p, int batch, cudaStream_t st) {
     int rc = MPB200_OK;
     if (p->mode == MPB200_MODE_FULL) {
         rc = full_pass(p, batch, nullptr, st);
+    } else if (p->mode == MPB200_MODE_SGRAM) {
+        const bool refresh = p->refresh_every > 0 && (p->iter + 1) % (unsigned)p->refresh_every == 0;
+        if (refresh) {
+            rc = full_pass(p, batch, p->map, st, true);
+        } else {
+            DeltaArgs d;
+            d.atomspec = p->atomspec;
+            d.pairspec2 = p->pairspec2;
+            d.upd = p->upd;
+            d.batch = batch;
+            d.npairs = p->npairs;
+            d.nloc = p->nloc;
+            d.map = p->map;
+            d.N = p->N;
+            d.NS = p->NS;
+            d.cap = p->bm_cap;
+            d.NB = p->NB;
+            d.blk_shift = p->blk_shift;
+            d.A = p->A;
+            d.tw1 = p->tw1b;
+            d.tw2 = p->tw2;
+            d.bm_val = p->bm_val;
+            d.bm_pos = p->bm_pos;
+            d.row_val = p->row_val;
+            d.row_pos = p->row_pos;
+            MPB_DISPATCH_M(p->M2, {
+                using F = BlockFft<MM, float>;
+                constexpr int TPB = F::T < 256 ? 256 : F::T;
+                constexpr int NT = TPB / F::T;
+                const size_t smem = (size_t)(256 + NT * F::SMEM_CPX) * sizeof(C32) +
+                                    (size_t)NT * 2 * p->bm_cap * sizeof(float);
+                static size_t allowed = 0;
+                if (smem > allowed) { MPB_CUDA(allow_smem(k_delta<MM>, smem)); allowed = smem; }
+                const int gx = (p->npairs + NT - 1) / NT;
+                int groups = (p->sm_count * 12 + gx - 1) / gx;
+                if (groups < 1) groups = 1;
+                if (groups > batch) groups = batch;
+                k_delta<MM><<<dim3(gx, groups), TPB, smem, st>>>(d);
+            });
+            MPB_LAUNCH_CHECK("k_delta");
+            mark(p, 4, st);
+            CorrArgs a = base_corr_args(p);
+            a.win = p->win_step;
+            a.nwin = batch;
+            a.nwin_ptr = p->trunc_count + (p->iter & 1u);
+            a.dense = p->map;
+            a.dense_row_stride = (long long)p->nloc * p->NS;
+            a.dense_atom_stride = p->NS;
+            a.dense_col_off = 0;
+            rc = launch_corr<MODE_DENSE | MODE_BLOCKMAX | MODE_ROWMAX>(p, a, corr_groups(p, batch), st);
+        }
     } else if (p->mode == MPB200_MODE_GRAM) {
         const bool refresh = p->refresh_every > 0 && (p->iter + 1) % (unsigned)p->refresh_every == 0;
         if (refresh) {
@@ -344,6 +401,20 @@ static int build_pair_spectra(Plan* p, cudaStream_t st) {
     return MPB200_OK;
 }
 
+// SGRAM tables: pair spectra at M2 and forward spectra of every atom left-padded by A-1 zeros.
+static int build_sgram_tables(Plan* p, cudaStream_t st) {
+    MPB_DISPATCH_M(p->M2, {
+        using F = BlockFft<MM, double>;
+        const size_t smem = (size_t)(F::SMEM_CPX + 256) * sizeof(cpx<double>);
+        static bool once = false;
+        if (!once) { MPB_CUDA((allow_smem(k_pair_spectra<MM, double>, smem))); once = true; }
+        k_pair_spectra<MM, double><<<p->npairs, F::T, smem, st>>>(p->dict, p->A, p->lo, p->hi, p->tw1bd, p->tw2d,
+                                                                   p->pairspec2);
+    });
+    MPB_LAUNCH_CHECK("k_pair_spectra");
+    return launch_window_fft_ex(p->M2, p->tw1b, p->tw2, p->dict, p->A, p->A, p->win_atoms, p->K, p->atomspec, st);
+}
+
 static int check_plan(Plan* p, bool need_dict) {
     if (!p) return fail(MPB200_EINVAL, "null plan");
     if (need_dict && !p->dict_set) return fail(MPB200_ESTATE, "mpb200_plan_set_dictionary has not been called");
@@ -373,7 +444,7 @@ int mpb200_plan_create(mpb200_plan_t* out, int n_atoms, int atom_size, int n_sam
     if (atom_lo == 0 && atom_hi == 0) atom_hi = n_atoms;
     if (atom_lo < 0 || atom_hi > n_atoms || atom_lo >= atom_hi)
         return fail(MPB200_EINVAL, "atom shard [atom_lo, atom_hi) must be a non-empty sub-range of [0, n_atoms)");
-    if (mode < MPB200_MODE_AUTO || mode > MPB200_MODE_FULL) return fail(MPB200_EINVAL, "unknown mode");
+    if (mode < MPB200_MODE_AUTO || mode > MPB200_MODE_SGRAM) return fail(MPB200_EINVAL, "unknown mode");
     const int M = choose_fft_size(atom_size);
     if (M == 0)
         return fail(MPB200_EINVAL, "atom_size " + std::to_string(atom_size) +
@@ -400,40 +471,74 @@ int mpb200_plan_create(mpb200_plan_t* out, int n_atoms, int atom_size, int n_sam
     p->blk_shift = 0;
     while ((1 << p->blk_shift) < p->blk) ++p->blk_shift;
     p->NB = (n_samples + p->blk - 1) / p->blk;
+    p->NS = n_samples;
     p->vfull = (M - atom_size + 1) / p->blk;
     if (p->vfull > 32) p->vfull = 32;
     p->nchunks = (p->NB + p->vfull - 1) / p->vfull;
     p->bm_cap = ((2 * atom_size - 2) / p->blk + 2) * p->blk;   // positions a step window can refresh
 
-    // Gram table: (nloc, K?) -- the table is indexed [winner atom (any of K)][owned atom][lag]
+    // GRAM table is indexed [winner atom (any of K)][owned atom][lag]
     const uint64_t gram_bytes = (uint64_t)n_atoms * p->nloc * (2ull * atom_size) * sizeof(float);
-    const uint64_t map_bytes = (uint64_t)max_batch * p->nloc * n_samples * sizeof(float);
+    const int ns_pad = (n_samples + 3) & ~3;   // SGRAM map rows are padded to 16 bytes (bulk-copy granularity)
+    const uint64_t map_row_bytes = (uint64_t)p->nloc * ns_pad * sizeof(float);             // per signal
+    const uint64_t map_bytes = (uint64_t)max_batch * map_row_bytes;
+    int M2 = 512;
+    while (M2 < 2 * atom_size) M2 *= 2;
+    const int nvb_max = (2 * atom_size - 2) / p->blk + 2;
+    size_t free_b = 0, total_b = 0;
+    MPB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    // per-signal bytes of the structures every mode keeps + the resident map
+    const uint64_t per_signal = map_row_bytes + (uint64_t)p->nloc * p->NB * 8 + (uint64_t)p->nloc * 8 +
+                                (uint64_t)n_samples * 4;
+    const uint64_t sgram_fixed = (uint64_t)n_atoms * M2 * 8 + (uint64_t)p->npairs * (M2 + M) * 8 +
+                                 (uint64_t)2048 * M * 8 + (uint64_t)n_atoms * atom_size * 4;
+    long long cap = (long long)(((double)free_b * 0.85 - (double)sgram_fixed) / (double)per_signal);
+    if (mode == MPB200_MODE_SGRAM && gram_budget_bytes) {   // explicit cap on the resident map
+        const long long c2 = (long long)(gram_budget_bytes / map_row_bytes);
+        if (c2 < cap) cap = c2;
+    }
+    if (cap > max_batch) cap = max_batch;
+    const bool sgram_ok = M2 <= 8192 && nvb_max <= 30 && cap >= 1;
     if (mode == MPB200_MODE_AUTO) {
         // GRAM when the table and the resident map fit AND the table build (K window transforms per
         // pair) is amortised by the batch: break-even is about K / max_batch iterations.
-        size_t free_b = 0, total_b = 0;
-        MPB_CUDA(cudaMemGetInfo(&free_b, &total_b));
         const uint64_t budget = gram_budget_bytes ? gram_budget_bytes : (uint64_t)(0.4 * (double)free_b);
         const bool fits = gram_bytes <= budget && gram_bytes + map_bytes <= (uint64_t)(0.8 * (double)free_b);
-        mode = (fits && (long long)max_batch * 16 >= n_atoms) ? MPB200_MODE_GRAM : MPB200_MODE_RECORRELATE;
+        if (fits && (long long)max_batch * 16 >= n_atoms && nvb_max <= 32) mode = MPB200_MODE_GRAM;
+        // SGRAM needs a resident sub-batch big enough to fill the chip: >= 32 signals, or the whole batch
+        else if (sgram_ok && (cap >= max_batch || cap >= 32)) mode = MPB200_MODE_SGRAM;
+        else mode = MPB200_MODE_RECORRELATE;
     }
     p->mode = mode;
     p->GS = 2 * atom_size;
-    if (mode == MPB200_MODE_GRAM && (2 * atom_size - 2) / p->blk + 2 > 32) {
+    p->M2 = M2;
+    p->Bcap = max_batch;
+    if (mode == MPB200_MODE_GRAM && nvb_max > 32) {
         free_plan(p);
         return fail(MPB200_EINVAL, "GRAM mode: window spans more than 32 blocks");
     }
+    if (mode == MPB200_MODE_SGRAM) {
+        if (!sgram_ok) {
+            free_plan(p);
+            return fail(MPB200_EINVAL, "SGRAM mode: atom too long for the Gram-row transform, or not even one "
+                                       "signal's correlation map fits in free device memory");
+        }
+        const long long n_sub = (max_batch + cap - 1) / cap;         // balanced sub-batches
+        p->Bcap = (int)((max_batch + n_sub - 1) / n_sub);
+        p->NS = ns_pad;
+    }
+    const int alloc_batch = p->Bcap;
 
     int rc = MPB200_OK;
     std::vector<cpx<float>> t1, t2;
     std::vector<cpx<double>> t1d, t2d;
     host_twiddles<float>(M, t1, t2);
     host_twiddles<double>(M, t1d, t2d);
-    const long long total_full = (long long)max_batch * p->nchunks;
+    const long long total_full = (long long)alloc_batch * p->nchunks;
     p->wcap = (int)(total_full < 2048 ? total_full : 2048);
-    if (p->wcap < max_batch) p->wcap = max_batch;
+    if (p->wcap < alloc_batch) p->wcap = alloc_batch;
     std::vector<Win> wf((size_t)total_full);
-    for (int b = 0; b < max_batch; ++b)
+    for (int b = 0; b < alloc_batch; ++b)
         for (int c = 0; c < p->nchunks; ++c) {
             Win w;
             w.row = b;
@@ -451,19 +556,19 @@ int mpb200_plan_create(mpb200_plan_t* out, int n_atoms, int atom_size, int n_sam
     MPB_TRY(dev_alloc(p, &p->tw2d, (size_t)256));
     MPB_TRY(dev_alloc(p, &p->winspec, (size_t)p->wcap * M));
     MPB_TRY(dev_alloc(p, &p->win_full, (size_t)total_full));
-    MPB_TRY(dev_alloc(p, &p->win_step, (size_t)max_batch));
-    MPB_TRY(dev_alloc(p, &p->bm_val, (size_t)max_batch * p->nloc * p->NB));
-    MPB_TRY(dev_alloc(p, &p->bm_pos, (size_t)max_batch * p->nloc * p->NB));
-    MPB_TRY(dev_alloc(p, &p->row_val, (size_t)max_batch * p->nloc));
-    MPB_TRY(dev_alloc(p, &p->row_pos, (size_t)max_batch * p->nloc));
-    MPB_TRY(dev_alloc(p, &p->residual, (size_t)max_batch * n_samples));
-    MPB_TRY(dev_alloc(p, &p->best, (size_t)max_batch));
+    MPB_TRY(dev_alloc(p, &p->win_step, (size_t)alloc_batch));
+    MPB_TRY(dev_alloc(p, &p->bm_val, (size_t)alloc_batch * p->nloc * p->NB));
+    MPB_TRY(dev_alloc(p, &p->bm_pos, (size_t)alloc_batch * p->nloc * p->NB));
+    MPB_TRY(dev_alloc(p, &p->row_val, (size_t)alloc_batch * p->nloc));
+    MPB_TRY(dev_alloc(p, &p->row_pos, (size_t)alloc_batch * p->nloc));
+    MPB_TRY(dev_alloc(p, &p->residual, (size_t)alloc_batch * n_samples));
+    MPB_TRY(dev_alloc(p, &p->best, (size_t)alloc_batch));
     std::vector<Win> wg;
     if (mode == MPB200_MODE_GRAM) {
         p->gram_bytes = gram_bytes;
         MPB_TRY(dev_alloc(p, &p->gram, (size_t)n_atoms * p->nloc * p->GS));
-        MPB_TRY(dev_alloc(p, &p->map, (size_t)max_batch * p->nloc * n_samples));
-        MPB_TRY(dev_alloc(p, &p->upd, (size_t)max_batch));
+        MPB_TRY(dev_alloc(p, &p->map, (size_t)alloc_batch * p->nloc * n_samples));
+        MPB_TRY(dev_alloc(p, &p->upd, (size_t)alloc_batch));
         MPB_TRY(dev_alloc(p, &p->trunc_count, (size_t)2));
         MPB_TRY(dev_alloc(p, &p->win_gram, (size_t)n_atoms));
         wg.resize((size_t)n_atoms);
@@ -473,6 +578,29 @@ int mpb200_plan_create(mpb200_plan_t* out, int n_atoms, int atom_size, int n_sam
             w.t0 = -(atom_size - 1);
             w.blk0 = 0;
             w.nvb = (2 * atom_size - 1 + p->blk - 1) / p->blk;
+            wg[(size_t)k] = w;
+        }
+    }
+    std::vector<cpx<float>> t1b, t2b;
+    std::vector<cpx<double>> t1bd, t2bd;
+    if (mode == MPB200_MODE_SGRAM) {
+        host_twiddles<float>(M2, t1b, t2b);
+        host_twiddles<double>(M2, t1bd, t2bd);
+        MPB_TRY(dev_alloc(p, &p->map, (size_t)alloc_batch * p->nloc * p->NS));
+        MPB_TRY(dev_alloc(p, &p->upd, (size_t)alloc_batch));
+        MPB_TRY(dev_alloc(p, &p->trunc_count, (size_t)2));
+        MPB_TRY(dev_alloc(p, &p->pairspec2, (size_t)p->npairs * M2));
+        MPB_TRY(dev_alloc(p, &p->atomspec, (size_t)n_atoms * M2));
+        MPB_TRY(dev_alloc(p, &p->tw1b, (size_t)M2));
+        MPB_TRY(dev_alloc(p, &p->tw1bd, (size_t)M2));
+        MPB_TRY(dev_alloc(p, &p->win_atoms, (size_t)n_atoms));
+        wg.resize((size_t)n_atoms);
+        for (int k = 0; k < n_atoms; ++k) {
+            Win w;
+            w.row = k;
+            w.t0 = -(atom_size - 1);
+            w.blk0 = 0;
+            w.nvb = 0;
             wg[(size_t)k] = w;
         }
     }
@@ -486,7 +614,12 @@ int mpb200_plan_create(mpb200_plan_t* out, int n_atoms, int atom_size, int n_sam
     up(p->tw1d, t1d.data(), t1d.size() * sizeof(t1d[0]));
     up(p->tw2d, t2d.data(), t2d.size() * sizeof(t2d[0]));
     up(p->win_full, wf.data(), wf.size() * sizeof(Win));
-    if (!wg.empty()) up(p->win_gram, wg.data(), wg.size() * sizeof(Win));
+    if (!wg.empty() && p->win_gram) up(p->win_gram, wg.data(), wg.size() * sizeof(Win));
+    if (!wg.empty() && p->win_atoms) up(p->win_atoms, wg.data(), wg.size() * sizeof(Win));
+    if (p->tw1b) {
+        up(p->tw1b, t1b.data(), t1b.size() * sizeof(t1b[0]));
+        up(p->tw1bd, t1bd.data(), t1bd.size() * sizeof(t1bd[0]));
+    }
     if (p->gram && e == cudaSuccess) e = cudaMemset(p->gram, 0, (size_t)n_atoms * p->nloc * p->GS * sizeof(float));
     if (e != cudaSuccess) {
         free_plan(p);
@@ -519,6 +652,8 @@ int mpb200_plan_info_get(mpb200_plan_t plan, mpb200_plan_info* info) {
     info->n_blocks = p->NB;
     info->atom_lo = p->lo;
     info->atom_hi = p->hi;
+    info->resident_batch = p->Bcap;
+    info->fft_size2 = p->mode == MPB200_MODE_SGRAM ? p->M2 : 0;
     info->device_bytes = p->bytes;
     info->gram_bytes = p->gram_bytes;
     return MPB200_OK;
@@ -569,6 +704,10 @@ static int set_dictionary_impl(mpb200_plan_t plan, const float* d, bool normaliz
         rc = build_gram(p, st);
         if (rc) return rc;
     }
+    if (p->mode == MPB200_MODE_SGRAM) {
+        rc = build_sgram_tables(p, st);
+        if (rc) return rc;
+    }
     p->dict_set = true;
     p->cur_batch = 0;
     return MPB200_OK;
@@ -608,13 +747,15 @@ int mpb200_begin(mpb200_plan_t plan, const float* signal, int batch, void* strea
     Plan* p = reinterpret_cast<Plan*>(plan);
     int rc = check_plan(p, true);
     if (rc) return rc;
-    if (batch < 1 || batch > p->Bmax) return fail(MPB200_EINVAL, "batch must be in [1, max_batch]");
+    if (batch < 1 || batch > p->Bcap)
+        return fail(MPB200_EINVAL, "batch must be in [1, resident_batch] for the step-wise interface (" +
+                                       std::to_string(p->Bcap) + " signals fit at once in this mode)");
     if (!signal) return fail(MPB200_EINVAL, "null signal");
     cudaStream_t st = (cudaStream_t)stream;
     MPB_CUDA(cudaMemcpyAsync(p->residual, signal, (size_t)batch * p->N * sizeof(float), cudaMemcpyDeviceToDevice, st));
     p->cur_batch = batch;
     p->iter = 0;
-    if (p->mode == MPB200_MODE_GRAM) {
+    if (p->mode == MPB200_MODE_GRAM || p->mode == MPB200_MODE_SGRAM) {
         MPB_CUDA(cudaMemsetAsync(p->trunc_count, 0, 2 * sizeof(int), st));
         return full_pass(p, batch, p->map, st, true);
     }
@@ -662,17 +803,11 @@ int mpb200_reduce_best(const mpb200_best* cand, int n_ranks, int batch, mpb200_b
     return MPB200_OK;
 }
 
-int mpb200_sparse_code(mpb200_plan_t plan, const float* signal, int batch, int n_steps, float* residual_out,
-                       int32_t* atom_out, int32_t* pos_out, float* val_out, void* stream) {
-    Plan* p = reinterpret_cast<Plan*>(plan);
-    if (n_steps < 0) return fail(MPB200_EINVAL, "n_steps must be >= 0");
-    if (n_steps > 0 && (!atom_out || !pos_out || !val_out)) return fail(MPB200_EINVAL, "null output");
-    if (p && (p->lo != 0 || p->hi != p->K))
-        return fail(MPB200_ESTATE, "mpb200_sparse_code needs a plan that owns every atom; "
-                                   "sharded plans use begin/local_best/apply");
-    cudaStream_t st = (cudaStream_t)stream;
-    if (p) mark(p, 0, st);
-    int rc = mpb200_begin(plan, signal, batch, stream);
+// One resident batch (<= Bcap signals) through begin + n_steps x (apply, refresh).
+static int pursue_resident(Plan* p, const float* signal, int batch, int n_steps, float* residual_out,
+                           int32_t* atom_out, int32_t* pos_out, float* val_out, cudaStream_t st) {
+    mark(p, 0, st);
+    int rc = mpb200_begin(reinterpret_cast<mpb200_plan_t>(p), signal, batch, (void*)st);
     if (rc) return rc;
     mark(p, 1, st);
     for (int s = 0; s < n_steps; ++s) {
@@ -691,6 +826,34 @@ int mpb200_sparse_code(mpb200_plan_t plan, const float* signal, int batch, int n
     if (residual_out)
         MPB_CUDA(cudaMemcpyAsync(residual_out, p->residual, (size_t)batch * p->N * sizeof(float),
                                  cudaMemcpyDeviceToDevice, st));
+    return MPB200_OK;
+}
+
+int mpb200_sparse_code(mpb200_plan_t plan, const float* signal, int batch, int n_steps, float* residual_out,
+                       int32_t* atom_out, int32_t* pos_out, float* val_out, void* stream) {
+    Plan* p = reinterpret_cast<Plan*>(plan);
+    int rc = check_plan(p, true);
+    if (rc) return rc;
+    if (n_steps < 0) return fail(MPB200_EINVAL, "n_steps must be >= 0");
+    if (n_steps > 0 && (!atom_out || !pos_out || !val_out)) return fail(MPB200_EINVAL, "null output");
+    if (batch < 1 || batch > p->Bmax) return fail(MPB200_EINVAL, "batch must be in [1, max_batch]");
+    if (!signal) return fail(MPB200_EINVAL, "null signal");
+    if (p->lo != 0 || p->hi != p->K)
+        return fail(MPB200_ESTATE, "mpb200_sparse_code needs a plan that owns every atom; "
+                                   "sharded plans use begin/local_best/apply");
+    cudaStream_t st = (cudaStream_t)stream;
+    // signals are independent problems: the map modes walk the batch in balanced resident sub-batches
+    const int n_sub = (batch + p->Bcap - 1) / p->Bcap;
+    const int per = (batch + n_sub - 1) / n_sub;
+    for (int b0 = 0; b0 < batch; b0 += per) {
+        const int nb = batch - b0 < per ? batch - b0 : per;
+        const size_t eo = (size_t)b0 * (size_t)n_steps;
+        rc = pursue_resident(p, signal + (size_t)b0 * p->N, nb, n_steps,
+                             residual_out ? residual_out + (size_t)b0 * p->N : nullptr,
+                             atom_out ? atom_out + eo : nullptr, pos_out ? pos_out + eo : nullptr,
+                             val_out ? val_out + eo : nullptr, st);
+        if (rc) return rc;
+    }
     return MPB200_OK;
 }
 
@@ -718,7 +881,9 @@ int mpb200_sparse_code_host(mpb200_plan_t plan, const float* signal_host, int ba
         p->ev_cap = ev;
     }
     MPB_CUDA(cudaMemcpyAsync(p->d_signal, signal_host, sig_bytes, cudaMemcpyHostToDevice, st));
-    rc = mpb200_sparse_code(plan, p->d_signal, batch, n_steps, nullptr, p->d_atom, p->d_pos, p->d_val, stream);
+    // the residual overwrites the staged signal (a sub-batch's input is consumed before its residual is stored)
+    rc = mpb200_sparse_code(plan, p->d_signal, batch, n_steps, residual_out_host ? p->d_signal : nullptr, p->d_atom,
+                            p->d_pos, p->d_val, stream);
     if (rc) return rc;
     if (n_steps > 0) {
         MPB_CUDA(cudaMemcpyAsync(atom_out_host, p->d_atom, ev * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -726,7 +891,7 @@ int mpb200_sparse_code_host(mpb200_plan_t plan, const float* signal_host, int ba
         MPB_CUDA(cudaMemcpyAsync(val_out_host, p->d_val, ev * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     if (residual_out_host)
-        MPB_CUDA(cudaMemcpyAsync(residual_out_host, p->residual, sig_bytes, cudaMemcpyDeviceToHost, st));
+        MPB_CUDA(cudaMemcpyAsync(residual_out_host, p->d_signal, sig_bytes, cudaMemcpyDeviceToHost, st));
     MPB_CUDA(cudaStreamSynchronize(st));
     return MPB200_OK;
 }
@@ -738,9 +903,15 @@ int mpb200_correlate(mpb200_plan_t plan, const float* signal, int batch, float* 
     if (batch < 1 || batch > p->Bmax) return fail(MPB200_EINVAL, "batch must be in [1, max_batch]");
     if (!signal || !fm_out) return fail(MPB200_EINVAL, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
-    MPB_CUDA(cudaMemcpyAsync(p->residual, signal, (size_t)batch * p->N * sizeof(float), cudaMemcpyDeviceToDevice, st));
     p->cur_batch = 0;
-    return full_pass(p, batch, fm_out, st);
+    for (int b0 = 0; b0 < batch; b0 += p->Bcap) {
+        const int nb = batch - b0 < p->Bcap ? batch - b0 : p->Bcap;
+        MPB_CUDA(cudaMemcpyAsync(p->residual, signal + (size_t)b0 * p->N, (size_t)nb * p->N * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, st));
+        rc = full_pass(p, nb, fm_out + (size_t)b0 * p->nloc * p->N, st);
+        if (rc) return rc;
+    }
+    return MPB200_OK;
 }
 
 // Scratch for k_select_dense partial winners: one growing buffer per device (never shrinks;

@@ -16,6 +16,9 @@ struct Plan {
     int lo = 0, hi = 0, nloc = 0, npairs = 0;       // owned atom range
     int M = 0, blk = 0, blk_shift = 0, NB = 0;      // window FFT size, block-max granularity
     int vfull = 0, nchunks = 0;                     // full pass: blocks per window, windows per signal
+    int Bcap = 0;                                   // signals resident at once (<= Bmax; map modes sub-batch)
+    int NS = 0;                                     // row stride of the resident map (N, or N padded to 4 in SGRAM)
+    int M2 = 0;                                     // SGRAM: transform length of the synthesised Gram rows (>= 2A)
     int wcap = 0;                                   // window-spectrum slots
     int bm_cap = 0;                                 // positions refreshed by one step window (staging size)
     int cur_batch = 0;                              // batch loaded by mpb200_begin (0 = none)
@@ -25,6 +28,11 @@ struct Plan {
     C32* pairspec = nullptr;        // (npairs, M)
     C32 *tw1 = nullptr, *tw2 = nullptr;
     cpx<double> *tw1d = nullptr, *tw2d = nullptr;
+    C32* pairspec2 = nullptr;       // SGRAM: (npairs, M2)
+    C32* atomspec = nullptr;        // SGRAM: (K, M2) forward spectra of [0^(A-1), d_k]
+    C32* tw1b = nullptr;            // BlockFft<M2> twiddles (fp32 / fp64)
+    cpx<double>* tw1bd = nullptr;
+    Win* win_atoms = nullptr;       // (K) windows over dictionary rows, t0 = -(A-1)
     C32* winspec = nullptr;         // (wcap, M)
     Win* win_full = nullptr;        // (Bmax * nchunks)
     Win* win_step = nullptr;        // (Bmax)

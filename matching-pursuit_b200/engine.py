@@ -67,6 +67,8 @@ class Plan:
         self.mode = MODE_NAMES[info.mode]
         self.fft_size, self.block, self.n_blocks = info.fft_size, info.block, info.n_blocks
         self.device_bytes = info.device_bytes
+        self.resident_batch = info.resident_batch   # signals processed at once (sub-batch of the map modes)
+        self.fft_size2 = info.fft_size2
         self.batch = 0
         self.dictionary_key = None   # set by callers that cache plans
 

@@ -35,7 +35,7 @@ def run_plan(signal, d, steps, mode="recorrelate", atom_range=None):
 # --------------------------------------------------------------------------
 # golden vectors from the live reference
 # --------------------------------------------------------------------------
-@pytest.mark.parametrize("mode", ["recorrelate", "full", "gram"])
+@pytest.mark.parametrize("mode", ["recorrelate", "full", "gram", "sgram"])
 @pytest.mark.parametrize("path", [p for p in SC_CASES if "lcn" not in p],
                          ids=[os.path.basename(p)[:-4] for p in SC_CASES if "lcn" not in p])
 def test_golden_sparse_code(path, mode):
@@ -114,7 +114,7 @@ def make_case(k, a, n, b, s, family):
     return sig, d
 
 
-@pytest.mark.parametrize("mode", ["recorrelate", "full", "gram"])
+@pytest.mark.parametrize("mode", ["recorrelate", "full", "gram", "sgram"])
 @pytest.mark.parametrize("case", CASES, ids=[f"K{c[0]}_A{c[1]}_N{c[2]}_B{c[3]}_{c[5]}" for c in CASES])
 def test_oracle_parity(case, mode):
     k, a, n, b, s, family = case
@@ -143,10 +143,51 @@ def test_gram_mode_long_run_against_oracle(refresh):
     assert int((tr.pos + a > n).sum()) > 0      # the case does contain truncated winners
 
 
+@pytest.mark.parametrize("refresh", [0, 50])
+def test_sgram_mode_long_run_against_oracle(refresh):
+    """Synthesised Gram rows (SGRAM) over 300 iterations, truncated winners included."""
+    k, a, n, b, s = 128, 256, 8192, 2, 300
+    d = O.make_dictionary(k, a, seed=11)
+    sig = torch.cat([O.make_planted_signals(d, 1, n, 150, seed=12), O.make_noise_signals(1, n, seed=13)], dim=0)
+    tr = O.greedy_pursuit(sig, d, s, want_margin=True)
+    plan = mpb.Plan(k, a, n, b, mode="sgram", device=DEV).set_dictionary(d).set_refresh_every(refresh)
+    assert plan.mode == "sgram" and plan.info.gram_bytes == 0 and plan.fft_size2 == 512
+    atom, pos, val, res = plan.sparse_code(sig.to(DEV), s)
+    checked = compare_with_oracle_trace(tr, atom.cpu().numpy(), pos.cpu().numpy(), val.cpu().numpy(),
+                                        res.cpu().numpy())
+    assert checked >= 100
+
+
+def test_sgram_sub_batches_equal_one_batch():
+    """A resident-map budget that holds 3 of 7 signals: the batch is walked in balanced sub-batches
+    and every signal gets the result it gets alone (signals are independent problems)."""
+    k, a, n, b, s = 24, 128, 4096, 7, 20
+    d = O.make_dictionary(k, a, seed=3)
+    sig = O.make_planted_signals(d, b, n, 12, seed=4)
+    whole = mpb.Plan(k, a, n, b, mode="sgram", device=DEV).set_dictionary(d)
+    assert whole.resident_batch == b
+    ref = [t.cpu() for t in whole.sparse_code(sig.to(DEV), s)]
+    part = mpb.Plan(k, a, n, b, mode="sgram", device=DEV, gram_budget_bytes=3 * k * n * 4 + 1024).set_dictionary(d)
+    assert part.resident_batch == 3
+    got = [t.cpu() for t in part.sparse_code(sig.to(DEV), s)]
+    for r, g in zip(ref, got):
+        assert torch.equal(r, g)
+    hatom, hpos, hval, hres = part.sparse_code_host(sig, s)
+    assert torch.equal(hatom, ref[0]) and torch.equal(hpos, ref[1]) and torch.equal(hval, ref[2])
+    assert torch.equal(hres, ref[3])
+    fm = part.correlate(sig.to(DEV)[:, 0])
+    assert torch.equal(fm.cpu(), whole.correlate(sig.to(DEV)[:, 0]).cpu())
+    with pytest.raises(mpb.MpbError):
+        part.begin(sig.to(DEV))      # the step-wise interface holds one resident batch
+
+
 def test_auto_mode_resolution():
     assert mpb.Plan(512, 1024, 2 ** 15, 64, device=DEV).mode == "gram"          # BASELINE configs[1]
-    assert mpb.Plan(512, 512, 2 ** 15, 1, device=DEV).mode == "recorrelate"      # table build not amortised
-    assert mpb.Plan(4096, 2048, 2 ** 15, 8, device=DEV).mode == "recorrelate"    # 275 GB table
+    assert mpb.Plan(512, 512, 2 ** 15, 1, device=DEV).mode == "sgram"           # table build not amortised
+    p = mpb.Plan(4096, 2048, 2 ** 15, 1024, device=DEV)                          # BASELINE configs[2]: 275 GB table
+    assert p.mode == "sgram" and 32 <= p.resident_batch < 1024
+    p.close()
+    assert mpb.Plan(4096, 2048, 2 ** 15, 8, device=DEV, mode="recorrelate").mode == "recorrelate"
 
 
 def test_config1_full_size():

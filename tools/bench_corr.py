@@ -33,8 +33,11 @@ for _ in range(args.reps):
 t = plan.timing_read()
 pairs = (args.atoms + 1) // 2
 corr_ms = t["recorrelate"][0] / max(t["recorrelate"][1], 1)
+upd_ms = t["gram_update"][0] / max(t["gram_update"][1], 1)
+rb = plan.resident_batch
 print(json.dumps({
-    "mode": plan.mode, "batch": args.batch, "fft_size": plan.fft_size,
+    "mode": plan.mode, "batch": args.batch, "resident_batch": rb, "fft_size": plan.fft_size, "fft_size2": plan.fft_size2,
+    "us_per_atom_step": 1e3 * (corr_ms + upd_ms + t["apply"][0] / max(t["apply"][1], 1)) / min(rb, args.batch),
     "recorrelate_ms_per_iteration": corr_ms,
     "ns_per_transform": 1e6 * corr_ms / (args.batch * pairs),
     "apply_ms": t["apply"][0] / max(t["apply"][1], 1),
