@@ -279,6 +279,16 @@ def run_atom_sharded(args):
         dist.destroy_process_group()
 
 
+def measured_traffic(kernel, workload, signals_per_launch):
+    """dram read+write bytes per launch of `kernel` from the committed `ncu --set full` capture
+    (profiles/traffic.json: bytes per signal of one launch, measured on this workload's shapes), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t[kernel][workload]["dram_bytes_per_signal"] * signals_per_launch
+    except Exception:
+        return None
+
+
 # --------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------
@@ -418,6 +428,27 @@ def main():
                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                     "peak_source": peak_src, "traffic": None, "alg_bytes_per_launch": gram_bytes,
                     "ms_per_launch": gram_ms / gram_n, "share_of_step": gram_ms / ms_total}
+    elif plan.mode == "sgram" and gram_n:
+        # dominant kernel in SGRAM mode: k_delta.  The Gram rows are synthesised from L2-resident spectra, so the
+        # algorithmic HBM bytes per atom-step are the map window read-modify-write alone: 8*K*W, W = 2A-1
+        # (SURVEY.md 8d "Gram incremental update" minus its 4*K*W table read).
+        w = 2 * a - 1
+        n_sub = -(-batch // plan.resident_batch)
+        per_launch_signals = batch / n_sub
+        delta_bytes = 8 * k * w * per_launch_signals
+        per_launch_s = gram_ms / gram_n / 1e3
+        achieved = delta_bytes / per_launch_s / 1e9
+        flops = per_launch_signals * ((k + 1) // 2) * 5.0 * plan.fft_size2 * (plan.fft_size2.bit_length() - 1)
+        roofline = {"bound": "hbm", "kernel": "k_delta (Gram rows synthesised by inverse FFT of cached spectra; TMA-staged "
+                                              "map window -= v * row; fused block/row maxima)",
+                    "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "peak_source": peak_src, "traffic": measured_traffic("k_delta", args.workload, per_launch_signals),
+                    "alg_bytes_per_launch": delta_bytes, "signals_per_launch": per_launch_signals,
+                    "ms_per_launch": gram_ms / gram_n, "share_of_step": gram_ms / ms_total,
+                    "fp32": {"note": "secondary bound: nominal 5*M2*log2(M2) FLOP per inverse transform against the "
+                                     "nominal (unmeasured) FP32 FMA peak",
+                             "achieved_tflops": flops / per_launch_s / 1e12,
+                             "nominal_peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12}}
     elif corr_n:
         per_launch_s = corr_ms / corr_n / 1e3
         achieved = alg_bytes / per_launch_s / 1e9
@@ -438,7 +469,8 @@ def main():
         "dtype": "f32", "data": "synthetic (planted atoms + noise, seeded; dictionary U(-1,1) unit-normed)",
         "config": {"workload": desc if standard else f"NON-STANDARD batch={batch} iterations={s} of: {desc}",
                    "batch_per_gpu": batch, "n_samples": n, "n_atoms": k, "atom_size": a, "iterations": s,
-                   "mode": plan.mode, "fft_size": m_fft, "block": blk,
+                   "mode": plan.mode, "fft_size": m_fft, "fft_size2": plan.fft_size2, "block": blk,
+                   "resident_batch": plan.resident_batch,
                    "parallelism": f"batch-sharded x{world}, no collective",
                    "l2": f"inputs larger than L2: plan working set {int(plan.device_bytes) >> 20} MiB + signals "
                          f"{batch * n * 4 >> 20} MiB"},

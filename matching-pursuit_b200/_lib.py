@@ -13,7 +13,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB_PATH = os.path.join(HERE, "libmpb200.so")
+# MPB200_LIBRARY points the binding at an alternative build of the same sources (A/B timing of kernel variants)
+LIB_PATH = os.environ.get("MPB200_LIBRARY") or os.path.join(HERE, "libmpb200.so")
 SOURCES = ["mpb200.cu", "fftconv.cu"]
 HEADERS = ["kernels.cuh", "fft_core.cuh", "bigfft.cuh", "types.h", "plan.h"]
 

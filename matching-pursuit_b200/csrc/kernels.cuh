@@ -27,7 +27,7 @@ constexpr int MODE_DENSE = 4;
 
 __device__ __forceinline__ C32 ld_stream(const C32* p) {
     float2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    asm("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));   // not volatile: free to batch
     return {v.x, v.y};
 }
 
@@ -749,14 +749,14 @@ __device__ __forceinline__ void warp_argmax_redux(float& v, int& at) {
 // positions), and the rows go back with bulk stores that overlap the block-max phase and the next
 // signal's transform.  No register ever waits on HBM.
 //
-// grid = (ceil(pairs / NT), signal groups); a CTA keeps its pair(s) and walks signals
-// b = blockIdx.y, blockIdx.y + gridDim.y, ...
+// Persistent grid (occupancy x SM count CTAs); work items are (pair group, signal) in pair-major order.
 // ---------------------------------------------------------------------------
 struct DeltaArgs {
     const C32* atomspec;    // (K, M2): forward spectrum of [0^(A-1), d_k]
     const C32* pairspec2;   // (npairs, M2): inverse-kernel spectrum of d[2q] + i d[2q+1], scaled 1/M2
     const GramUpdate* upd;  // (B)
     int batch, npairs, nloc;
+    int ngroups;            // ceil(npairs / transforms per CTA)
     float* map;             // (B, nloc, NS)
     int N, NS, NB, blk_shift, A;
     int cap;                // staged positions per row (bm_cap: whole blocks covering any +-A window)
@@ -771,6 +771,12 @@ struct DeltaArgs {
 #ifndef MPB_DELTA_MINB
 #define MPB_DELTA_MINB 3
 #endif
+#ifndef MPB_DELTA_LEAN_RMW
+#define MPB_DELTA_LEAN_RMW 1
+#endif
+#ifndef MPB_DELTA_LEAN_BM
+#define MPB_DELTA_LEAN_BM 1
+#endif
 template <int M2>
 __global__ void __launch_bounds__((BlockFft<M2, float>::T < 256 ? 256 : BlockFft<M2, float>::T), MPB_DELTA_MINB)
 k_delta(const DeltaArgs a) {
@@ -778,6 +784,8 @@ k_delta(const DeltaArgs a) {
     constexpr int TPB = F::T < 256 ? 256 : F::T;
     constexpr int NT = TPB / F::T;
     constexpr int NW = F::T / 32;
+    constexpr int RW0 = NW >= 4 ? NW - 2 : 0;            // first of the warps that re-derive the row maxima
+    constexpr int NROW = NW >= 2 ? 1 : 2;                // rows per such warp
     extern __shared__ __align__(16) unsigned char smraw[];
     C32* stw2 = reinterpret_cast<C32*>(smraw);
     const int sb = threadIdx.x / F::T, tl = threadIdx.x % F::T;
@@ -794,20 +802,33 @@ k_delta(const DeltaArgs a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
     }
-
-    int q = blockIdx.x * NT + sb;
-    const bool q_ok = q < a.npairs;
-    if (!q_ok) q = a.npairs - 1;
-    const C32* __restrict__ Eq = a.pairspec2 + (size_t)q * M2;
-    const bool second = 2 * q + 1 < a.nloc;
     const int blk = 1 << a.blk_shift;
     const int warp = tl >> 5, lane = tl & 31;
+    const int which0 = warp - RW0;                       // row (0/1) this warp re-derives; outside [0, 2): none
     unsigned phase = 0;
     __syncthreads();
 
-    for (int b = blockIdx.y; b < a.batch; b += gridDim.y) {
+    // Work items (pair group g, signal b), g-major so that a CTA keeps its pair spectra hot; the
+    // grid is persistent and every CTA takes an equal contiguous share.  The loop is software
+    // pipelined: the spectra of the NEXT item are requested into the (dead) FFT registers right
+    // after the map update, so their L2 latency is covered by the block-max / row-max phases.
+    const long long total = (long long)a.ngroups * a.batch;
+    const long long it1 = total * (blockIdx.x + 1) / gridDim.x;
+    long long it = total * blockIdx.x / gridDim.x;
+    auto next_valid = [&](long long i) {                 // first item >= i whose signal takes the Gram route
+        while (i < it1 && !a.upd[(int)(i % a.batch)].valid) ++i;
+        return i;
+    };
+    C32 r[F::E];
+    it = next_valid(it);
+    while (it < it1) {
+        const int g = (int)(it / a.batch), b = (int)(it - (long long)g * a.batch);
+        const long long it_next = next_valid(it + 1);
         const GramUpdate u = a.upd[b];
-        if (!u.valid) continue;                          // CTA-uniform: this signal takes the FFT route
+        int q = g * NT + sb;
+        const bool q_ok = q < a.npairs;
+        if (!q_ok) q = a.npairs - 1;
+        const bool second = 2 * q + 1 < a.nloc;
         const int p = u.position;
         const float nv = -u.value;
         const int first = max(0, p - a.A + 1), last = p + a.A - 1;     // valid => p + A <= N
@@ -817,20 +838,38 @@ k_delta(const DeltaArgs a) {
         float* __restrict__ m0 = a.map + ((size_t)b * a.nloc + 2 * q) * a.NS + start;
         float* __restrict__ m1 = m0 + a.NS;
         if (tl == 0 && q_ok) {
-            bulk_wait_read0();                           // the previous signal's stores have left the staging rows
+            bulk_wait_read0();                           // the previous item's stores have left the staging rows
             const unsigned bytes = (unsigned)cnt * 4u;
             mbar_expect_tx(bar, second ? 2u * bytes : bytes);
             bulk_load(st0, m0, bytes, bar);
             if (second) bulk_load(st1, m1, bytes, bar);
         }
-        const C32* __restrict__ S = a.atomspec + (size_t)u.atom * M2;
-        C32 r[F::E];
+        // the old row maxima are fetched now so that the row phase at the end never waits on memory
+        float old_v[NROW];
+        int old_p[NROW];
 #pragma unroll
-        for (int e = 0; e < F::E; ++e) {
-            const int j = F::in_index(tl, e);
-            const float2 ev = __ldg(reinterpret_cast<const float2*>(Eq + j));
-            const float2 sv = __ldg(reinterpret_cast<const float2*>(S + j));
-            r[e] = cmul(C32{sv.x, sv.y}, C32{ev.x, ev.y});
+        for (int i = 0; i < NROW; ++i) {
+            const int which = which0 + i;
+            const bool mine = q_ok && which >= 0 && which < 2 && (which == 0 || second);
+            const size_t rowi = (size_t)b * a.nloc + 2 * q + (mine ? which : 0);
+            old_v[i] = mine ? __ldg(a.row_val + rowi) : 0.f;
+            old_p[i] = mine ? __ldg(a.row_pos + rowi) : 0;
+        }
+        {
+            // Both spectra are L2 resident (the pair spectrum is re-read by this CTA for every signal,
+            // the winner spectrum by every CTA).  Measured dead ends, for the record: requesting the next
+            // item's winner spectrum into the dead FFT registers before the block-max phase (spills:
+            // 5.35 -> 5.99 ms per iteration of 128 signals), and parking the pair spectrum in tensor
+            // memory with tcgen05.st/ld.32x32b (correct, but 14.7 ms).
+            const C32* __restrict__ Eq = a.pairspec2 + (size_t)q * M2;
+            const C32* __restrict__ S = a.atomspec + (size_t)u.atom * M2;
+#pragma unroll
+            for (int e = 0; e < F::E; ++e) {
+                const int j = F::in_index(tl, e);
+                const float2 y = __ldg(reinterpret_cast<const float2*>(Eq + j));
+                const float2 x = __ldg(reinterpret_cast<const float2*>(S + j));
+                r[e] = cmul(C32{x.x, x.y}, C32{y.x, y.y});
+            }
         }
         F::template pass1<1>(r, tl, sm, a.tw1);
         __syncthreads();
@@ -841,16 +880,33 @@ k_delta(const DeltaArgs a) {
         if (q_ok) {
             while (!mbar_try_wait(bar, phase)) {}
             phase ^= 1u;
-            // output m is lag m - (A-1), i.e. position t = p - (A-1) + m, staged at index t - start
+            // output m is lag m - (A-1), i.e. position t = p - (A-1) + m, staged at index i = m + off.
+            // Valid outputs are m < 2A-1 with t >= 0:  i in [lo_i, hi_i).  The staging rows hold
+            // cap >= M2 + blk floats, so when off >= 0 every index is in bounds and only the store
+            // has to be predicated.
             const int off = p - (a.A - 1) - start;
-            const int mmax = 2 * a.A - 1;
+            const int lo_i = max(off, 0), hi_i = off + 2 * a.A - 1;
+            const unsigned span = (unsigned)(hi_i - lo_i);
+            const int i0 = F::out_index(tl, 0) + off;
+            if (MPB_DELTA_LEAN_RMW && off >= 0) {
 #pragma unroll
-            for (int e = 0; e < F::E; ++e) {
-                const int m = F::out_index(tl, e);
-                const int i = m + off;
-                if (m < mmax && i >= 0) {
-                    st0[i] = fmaf(nv, r[e].x, st0[i]);
-                    if (second) st1[i] = fmaf(nv, r[e].y, st1[i]);
+                for (int e = 0; e < F::E; ++e) {
+                    const int i = i0 + (F::out_index(0, e) - F::out_index(0, 0));
+                    const float x0 = fmaf(nv, r[e].x, st0[i]);
+                    const float x1 = fmaf(nv, r[e].y, st1[i]);
+                    if ((unsigned)(i - lo_i) < span) {
+                        st0[i] = x0;
+                        st1[i] = x1;                     // row 1 of a last odd pair is staged garbage, never stored back
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < F::E; ++e) {
+                    const int i = i0 + (F::out_index(0, e) - F::out_index(0, 0));
+                    if ((unsigned)(i - lo_i) < span) {
+                        st0[i] = fmaf(nv, r[e].x, st0[i]);
+                        st1[i] = fmaf(nv, r[e].y, st1[i]);
+                    }
                 }
             }
             fence_proxy_async();                         // generic-proxy writes -> visible to the bulk stores
@@ -862,48 +918,50 @@ k_delta(const DeltaArgs a) {
             bulk_commit();
         }
         if (q_ok) {
+            // (row, block) tasks are dealt round-robin to the warps; the refreshed (max, position) pairs
+            // only go to shared memory here -- the row warps publish them to bm_val / bm_pos.
             const int ntask = second ? 2 * nvb : nvb;
-            for (int task = warp; task < ntask; task += NW) {
-                const int which = task >= nvb ? 1 : 0;
-                const int i = task - which * nvb;
-                const float* __restrict__ row = (which ? st1 : st0) + (i << a.blk_shift);
-                const int t0 = start + (i << a.blk_shift);
-                const int lim = a.N - t0;                // positions j >= lim are beyond the signal
-                float v = -INFINITY;
+            int which = 0, i = warp;
+            for (int task = warp; task < ntask; task += NW, i += NW) {
+                if (i >= nvb) { i -= nvb; which = 1; }
+                const float* __restrict__ row = st0 + which * a.cap + (i << a.blk_shift);
+                const int jbase = i << a.blk_shift;      // position of row[0] relative to `start`
+                const int lim = a.N - start - jbase;     // positions j >= lim are beyond the signal
+                float v;
                 int at = INT_MAX;
-                if (blk >= 128) {
-                    for (int j = 4 * lane; j < blk; j += 128) {
-                        const float4 c = *reinterpret_cast<const float4*>(row + j);
-                        if (j + 3 < lim) {
-                            if (c.x > v) { v = c.x; at = j; }
-                            if (c.y > v) { v = c.y; at = j + 1; }
-                            if (c.z > v) { v = c.z; at = j + 2; }
-                            if (c.w > v) { v = c.w; at = j + 3; }
-                        } else {
-                            if (j < lim && c.x > v) { v = c.x; at = j; }
-                            if (j + 1 < lim && c.y > v) { v = c.y; at = j + 1; }
-                            if (j + 2 < lim && c.z > v) { v = c.z; at = j + 2; }
-                        }
-                    }
+                if (MPB_DELTA_LEAN_BM && blk == 256 && lim >= 256) {     // the common shape: two float4 per lane
+                    const float4 c0 = *reinterpret_cast<const float4*>(row + 4 * lane);
+                    const float4 c1 = *reinterpret_cast<const float4*>(row + 128 + 4 * lane);
+                    v = fmaxf(fmaxf(fmaxf(c0.x, c0.y), fmaxf(c0.z, c0.w)), fmaxf(fmaxf(c1.x, c1.y), fmaxf(c1.z, c1.w)));
+                    const int kmax = __reduce_max_sync(0xffffffffu, float_key(v));
+                    v = __int_as_float(kmax ^ ((kmax >> 31) & 0x7fffffff));
+                    const int j = 4 * lane;              // descending order: the lowest matching position survives
+                    at = (c1.w + 0.0f == v) ? j + 131 : at;
+                    at = (c1.z + 0.0f == v) ? j + 130 : at;
+                    at = (c1.y + 0.0f == v) ? j + 129 : at;
+                    at = (c1.x + 0.0f == v) ? j + 128 : at;
+                    at = (c0.w + 0.0f == v) ? j + 3 : at;
+                    at = (c0.z + 0.0f == v) ? j + 2 : at;
+                    at = (c0.y + 0.0f == v) ? j + 1 : at;
+                    at = (c0.x + 0.0f == v) ? j : at;
+                    at = __reduce_min_sync(0xffffffffu, at);
                 } else {
+                    v = -INFINITY;
                     for (int j = lane; j < blk; j += 32) {
                         const float c = row[j];
                         if (j < lim && c > v) { v = c; at = j; }
                     }
+                    warp_argmax_redux(v, at);
                 }
-                warp_argmax_redux(v, at);
-                if (lane == 0) {
-                    const int pos = (at == INT_MAX) ? INT_MAX : t0 + at;
-                    const size_t o = ((size_t)b * a.nloc + 2 * q + which) * a.NB + blk0 + i;
-                    a.bm_val[o] = v;
-                    a.bm_pos[o] = pos;
-                    sBV[which * 32 + i] = make_float2(v, __int_as_float(pos));
-                }
+                if (lane == 0)
+                    sBV[which * 32 + i] = make_float2(v, __int_as_float(at == INT_MAX ? INT_MAX : start + jbase + at));
             }
         }
         __syncthreads();   // block maxima staged; nobody reads the staging rows any more
-        for (int which = warp; which < 2; which += NW) {
-            if (!q_ok || (which == 1 && !second)) continue;
+#pragma unroll
+        for (int wi = 0; wi < NROW; ++wi) {
+            const int which = which0 + wi;
+            if (!q_ok || which < 0 || which > 1 || (which == 1 && !second)) continue;
             const size_t rowi = (size_t)b * a.nloc + 2 * q + which;
             const size_t o = rowi * a.NB;
             float v = -INFINITY;
@@ -912,13 +970,13 @@ k_delta(const DeltaArgs a) {
                 const float2 c = sBV[which * 32 + lane];
                 v = c.x;
                 at = __float_as_int(c.y);
+                a.bm_val[o + blk0 + lane] = v;           // coalesced publication of the refreshed blocks
+                a.bm_pos[o + blk0 + lane] = at;
             }
-            const float old_v = a.row_val[rowi];
-            const int old_p = a.row_pos[rowi];
-            const int old_b = old_p >> a.blk_shift;
+            const int old_b = old_p[wi] >> a.blk_shift;
             const bool old_ok = old_b < blk0 || old_b >= blk0 + nvb;
             if (old_ok) {
-                if (lane == 31) take_better(v, at, old_v, old_p);       // nvb <= 30: lane 31 is free
+                if (lane == 31) take_better(v, at, old_v[wi], old_p[wi]);   // nvb <= 30: lane 31 is free
             } else {
                 for (int i = lane; i < a.NB; i += 32) {
                     if (i >= blk0 && i < blk0 + nvb) continue;
@@ -936,10 +994,11 @@ k_delta(const DeltaArgs a) {
                 a.row_pos[rowi] = (at == INT_MAX) ? 0 : at;
             }
         }
-        // the next signal's bulk loads are issued by tl == 0 (warp 0), which has passed the row phase
-        // itself; warps running ahead only touch the FFT buffer until the next barrier.
+        // the next item's bulk loads are issued by tl == 0 after the barrier above; warps running
+        // ahead only touch the FFT buffer until the next barrier.
+        it = it_next;
     }
-    if (tl == 0 && q_ok) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
+    if (tl == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
 }
 
 // ---------------------------------------------------------------------------

@@ -280,7 +280,7 @@ static int step_refresh(Plan* p, int batch, cudaStream_t st) {
             d.map = p->map;
             d.N = p->N;
             d.NS = p->NS;
-            d.cap = p->bm_cap;
+            d.cap = p->bm_cap > p->M2 + p->blk ? p->bm_cap : p->M2 + p->blk;   // see k_delta: in-bounds update indices
             d.NB = p->NB;
             d.blk_shift = p->blk_shift;
             d.A = p->A;
@@ -295,14 +295,18 @@ static int step_refresh(Plan* p, int batch, cudaStream_t st) {
                 constexpr int TPB = F::T < 256 ? 256 : F::T;
                 constexpr int NT = TPB / F::T;
                 const size_t smem = (size_t)(256 + NT * F::SMEM_CPX) * sizeof(C32) +
-                                    (size_t)NT * 2 * p->bm_cap * sizeof(float);
+                                    (size_t)NT * 2 * d.cap * sizeof(float);
                 static size_t allowed = 0;
                 if (smem > allowed) { MPB_CUDA(allow_smem(k_delta<MM>, smem)); allowed = smem; }
-                const int gx = (p->npairs + NT - 1) / NT;
-                int groups = (p->sm_count * 12 + gx - 1) / gx;
-                if (groups < 1) groups = 1;
-                if (groups > batch) groups = batch;
-                k_delta<MM><<<dim3(gx, groups), TPB, smem, st>>>(d);
+                if (p->delta_occ == 0) {
+                    MPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->delta_occ, k_delta<MM>, TPB, smem));
+                    if (p->delta_occ < 1) p->delta_occ = 1;
+                }
+                d.ngroups = (p->npairs + NT - 1) / NT;
+                const long long items = (long long)d.ngroups * batch;
+                long long ctas = (long long)p->sm_count * p->delta_occ;
+                if (ctas > items) ctas = items;
+                k_delta<MM><<<(unsigned)ctas, TPB, smem, st>>>(d);
             });
             MPB_LAUNCH_CHECK("k_delta");
             mark(p, 4, st);

@@ -18,6 +18,7 @@ struct Plan {
     int vfull = 0, nchunks = 0;                     // full pass: blocks per window, windows per signal
     int Bcap = 0;                                   // signals resident at once (<= Bmax; map modes sub-batch)
     int NS = 0;                                     // row stride of the resident map (N, or N padded to 4 in SGRAM)
+    int delta_occ = 0;                              // SGRAM: resident CTAs per SM of k_delta (persistent grid)
     int M2 = 0;                                     // SGRAM: transform length of the synthesised Gram rows (>= 2A)
     int wcap = 0;                                   // window-spectrum slots
     int bm_cap = 0;                                 // positions refreshed by one step window (staging size)
