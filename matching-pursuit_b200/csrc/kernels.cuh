@@ -771,12 +771,6 @@ struct DeltaArgs {
 #ifndef MPB_DELTA_MINB
 #define MPB_DELTA_MINB 3
 #endif
-#ifndef MPB_DELTA_LEAN_RMW
-#define MPB_DELTA_LEAN_RMW 1
-#endif
-#ifndef MPB_DELTA_LEAN_BM
-#define MPB_DELTA_LEAN_BM 1
-#endif
 template <int M2>
 __global__ void __launch_bounds__((BlockFft<M2, float>::T < 256 ? 256 : BlockFft<M2, float>::T), MPB_DELTA_MINB)
 k_delta(const DeltaArgs a) {
@@ -809,21 +803,18 @@ k_delta(const DeltaArgs a) {
     __syncthreads();
 
     // Work items (pair group g, signal b), g-major so that a CTA keeps its pair spectra hot; the
-    // grid is persistent and every CTA takes an equal contiguous share.  The loop is software
-    // pipelined: the spectra of the NEXT item are requested into the (dead) FFT registers right
-    // after the map update, so their L2 latency is covered by the block-max / row-max phases.
+    // grid is persistent and every CTA takes an equal contiguous share (host: ngroups * batch < 2^31).
     const long long total = (long long)a.ngroups * a.batch;
-    const long long it1 = total * (blockIdx.x + 1) / gridDim.x;
-    long long it = total * blockIdx.x / gridDim.x;
-    auto next_valid = [&](long long i) {                 // first item >= i whose signal takes the Gram route
-        while (i < it1 && !a.upd[(int)(i % a.batch)].valid) ++i;
-        return i;
-    };
+    int n_items = (int)(total * (blockIdx.x + 1) / gridDim.x - total * blockIdx.x / gridDim.x);
+    int g, b;
+    {
+        const long long it0 = total * blockIdx.x / gridDim.x;
+        g = (int)(it0 / a.batch);
+        b = (int)(it0 - (long long)g * a.batch);
+    }
     C32 r[F::E];
-    it = next_valid(it);
-    while (it < it1) {
-        const int g = (int)(it / a.batch), b = (int)(it - (long long)g * a.batch);
-        const long long it_next = next_valid(it + 1);
+    for (; n_items > 0; --n_items, b = (b + 1 == a.batch ? 0 : b + 1), g += (b == 0)) {
+        if (!a.upd[b].valid) continue;                   // CTA-uniform: this signal takes the FFT route
         const GramUpdate u = a.upd[b];
         int q = g * NT + sb;
         const bool q_ok = q < a.npairs;
@@ -888,7 +879,18 @@ k_delta(const DeltaArgs a) {
             const int lo_i = max(off, 0), hi_i = off + 2 * a.A - 1;
             const unsigned span = (unsigned)(hi_i - lo_i);
             const int i0 = F::out_index(tl, 0) + off;
-            if (MPB_DELTA_LEAN_RMW && off >= 0) {
+            if (off >= 0 && 2 * a.A >= M2) {             // power-of-two atoms away from the left edge: only output M2-1 is void
+#pragma unroll
+                for (int e = 0; e < F::E; ++e) {
+                    const int i = i0 + (F::out_index(0, e) - F::out_index(0, 0));
+                    const float x0 = fmaf(nv, r[e].x, st0[i]);
+                    const float x1 = fmaf(nv, r[e].y, st1[i]);
+                    if (F::out_index(F::T - 1, e) != M2 - 1 || tl != F::T - 1) {
+                        st0[i] = x0;
+                        st1[i] = x1;                     // row 1 of a last odd pair is staged garbage, never stored back
+                    }
+                }
+            } else if (off >= 0) {
 #pragma unroll
                 for (int e = 0; e < F::E; ++e) {
                     const int i = i0 + (F::out_index(0, e) - F::out_index(0, 0));
@@ -896,7 +898,7 @@ k_delta(const DeltaArgs a) {
                     const float x1 = fmaf(nv, r[e].y, st1[i]);
                     if ((unsigned)(i - lo_i) < span) {
                         st0[i] = x0;
-                        st1[i] = x1;                     // row 1 of a last odd pair is staged garbage, never stored back
+                        st1[i] = x1;
                     }
                 }
             } else {
@@ -921,40 +923,52 @@ k_delta(const DeltaArgs a) {
             // (row, block) tasks are dealt round-robin to the warps; the refreshed (max, position) pairs
             // only go to shared memory here -- the row warps publish them to bm_val / bm_pos.
             const int ntask = second ? 2 * nvb : nvb;
-            int which = 0, i = warp;
-            for (int task = warp; task < ntask; task += NW, i += NW) {
-                if (i >= nvb) { i -= nvb; which = 1; }
-                const float* __restrict__ row = st0 + which * a.cap + (i << a.blk_shift);
-                const int jbase = i << a.blk_shift;      // position of row[0] relative to `start`
-                const int lim = a.N - start - jbase;     // positions j >= lim are beyond the signal
-                float v;
-                int at = INT_MAX;
-                if (MPB_DELTA_LEAN_BM && blk == 256 && lim >= 256) {     // the common shape: two float4 per lane
-                    const float4 c0 = *reinterpret_cast<const float4*>(row + 4 * lane);
-                    const float4 c1 = *reinterpret_cast<const float4*>(row + 128 + 4 * lane);
-                    v = fmaxf(fmaxf(fmaxf(c0.x, c0.y), fmaxf(c0.z, c0.w)), fmaxf(fmaxf(c1.x, c1.y), fmaxf(c1.z, c1.w)));
+            if (blk == 256 && start + (nvb << 8) <= a.N) {       // the common shape: whole blocks, two float4 per lane
+                const float* __restrict__ rowl = st0 + 4 * lane;
+                int o = warp << 8, slot = warp;                   // offset into the staging rows, slot in sBV
+                for (int task = warp; task < ntask; task += NW, o += NW << 8, slot += NW) {
+                    if (task >= nvb && task - NW < nvb) {         // crossing from row 0 to row 1
+                        o += a.cap - (nvb << 8);
+                        slot += 32 - nvb;
+                    }
+                    const float4 c0 = *reinterpret_cast<const float4*>(rowl + o);
+                    const float4 c1 = *reinterpret_cast<const float4*>(rowl + o + 128);
+                    float v = fmaxf(fmaxf(fmaxf(c0.x, c0.y), fmaxf(c0.z, c0.w)),
+                                    fmaxf(fmaxf(c1.x, c1.y), fmaxf(c1.z, c1.w)));
                     const int kmax = __reduce_max_sync(0xffffffffu, float_key(v));
                     v = __int_as_float(kmax ^ ((kmax >> 31) & 0x7fffffff));
-                    const int j = 4 * lane;              // descending order: the lowest matching position survives
-                    at = (c1.w + 0.0f == v) ? j + 131 : at;
-                    at = (c1.z + 0.0f == v) ? j + 130 : at;
-                    at = (c1.y + 0.0f == v) ? j + 129 : at;
-                    at = (c1.x + 0.0f == v) ? j + 128 : at;
-                    at = (c0.w + 0.0f == v) ? j + 3 : at;
-                    at = (c0.z + 0.0f == v) ? j + 2 : at;
-                    at = (c0.y + 0.0f == v) ? j + 1 : at;
-                    at = (c0.x + 0.0f == v) ? j : at;
-                    at = __reduce_min_sync(0xffffffffu, at);
-                } else {
-                    v = -INFINITY;
+                    int at = INT_MAX;                             // descending order: the lowest matching position survives
+                    at = (c1.w + 0.0f == v) ? 131 : at;
+                    at = (c1.z + 0.0f == v) ? 130 : at;
+                    at = (c1.y + 0.0f == v) ? 129 : at;
+                    at = (c1.x + 0.0f == v) ? 128 : at;
+                    at = (c0.w + 0.0f == v) ? 3 : at;
+                    at = (c0.z + 0.0f == v) ? 2 : at;
+                    at = (c0.y + 0.0f == v) ? 1 : at;
+                    at = (c0.x + 0.0f == v) ? 0 : at;
+                    at = __reduce_min_sync(0xffffffffu, at == INT_MAX ? at : at + 4 * lane);
+                    // position = start + (block index within its row) * 256 + at
+                    if (lane == 0)
+                        sBV[slot] = make_float2(v, __int_as_float(at == INT_MAX ? INT_MAX
+                                                                                 : start + ((slot & 31) << 8) + at));
+                }
+            } else {
+                int which = 0, i = warp;
+                for (int task = warp; task < ntask; task += NW, i += NW) {
+                    if (i >= nvb) { i -= nvb; which = 1; }
+                    const float* __restrict__ row = st0 + which * a.cap + (i << a.blk_shift);
+                    const int jbase = i << a.blk_shift;      // position of row[0] relative to `start`
+                    const int lim = a.N - start - jbase;     // positions j >= lim are beyond the signal
+                    float v = -INFINITY;
+                    int at = INT_MAX;
                     for (int j = lane; j < blk; j += 32) {
                         const float c = row[j];
                         if (j < lim && c > v) { v = c; at = j; }
                     }
                     warp_argmax_redux(v, at);
+                    if (lane == 0)
+                        sBV[which * 32 + i] = make_float2(v, __int_as_float(at == INT_MAX ? INT_MAX : start + jbase + at));
                 }
-                if (lane == 0)
-                    sBV[which * 32 + i] = make_float2(v, __int_as_float(at == INT_MAX ? INT_MAX : start + jbase + at));
             }
         }
         __syncthreads();   // block maxima staged; nobody reads the staging rows any more
@@ -996,7 +1010,6 @@ k_delta(const DeltaArgs a) {
         }
         // the next item's bulk loads are issued by tl == 0 after the barrier above; warps running
         // ahead only touch the FFT buffer until the next barrier.
-        it = it_next;
     }
     if (tl == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
 }
