@@ -226,7 +226,7 @@ def run_atom_sharded(args):
     if args.iterations:
         s = args.iterations
     d, sig = make_inputs(torch, mpb, dev, batch, n, k, a, n_events=min(s, 1024), seed=1)   # same on every rank
-    pursuit = AtomShardedPursuit(k, a, n, batch, device=dev).set_dictionary(d)
+    pursuit = AtomShardedPursuit(k, a, n, batch, device=dev, mode=args.mode).set_dictionary(d)
 
     def barrier():
         if world > 1:
@@ -266,7 +266,7 @@ def run_atom_sharded(args):
             "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic (planted atoms + noise, seeded)",
-            "config": {"workload": desc, "iterations": s, "atoms_per_rank": (k + world - 1) // world,
+            "config": {"workload": desc, "iterations": s, "atoms_per_rank": (k + world - 1) // world, "mode": pursuit.engine.plan.mode,
                        "parallelism": f"atom-sharded x{world}"},
             "gpu_launches": int(launches), "ranks_agree": agree,
             "exchange_latency_ms": {"mean": sum(ex) / max(len(ex), 1), "p50": ex[len(ex) // 2] if ex else None,

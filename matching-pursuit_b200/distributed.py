@@ -59,7 +59,7 @@ def gather_results(local: torch.Tensor, batch: int, group=None) -> torch.Tensor:
 class PlanEngine:
     """The CUDA engine behind :class:`AtomShardedPursuit` (default)."""
 
-    def __init__(self, n_atoms, atom_size, n_samples, batch, lo, hi, device=None, mode="recorrelate"):
+    def __init__(self, n_atoms, atom_size, n_samples, batch, lo, hi, device=None, mode="auto"):
         from .engine import Plan, reduce_best
         self.plan = Plan(n_atoms, atom_size, n_samples, batch, mode=mode, atom_range=(lo, hi), device=device)
         self._reduce = reduce_best
@@ -95,7 +95,7 @@ class AtomShardedPursuit:
     """
 
     def __init__(self, n_atoms: int, atom_size: int, n_samples: int, batch: int, group=None, engine=None,
-                 device=None, mode: str = "recorrelate"):
+                 device=None, mode: str = "auto"):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
