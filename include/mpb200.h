@@ -222,6 +222,15 @@ int mpb200_fft_convolve(const float* const* operands, const int32_t* const* row_
                         const int32_t* operand_rows, int n_ops, int rows_out, int n, int conj_mask,
                         float scale, float* out, void* stream);
 
+/* y = irfft(mask(rfft(pad(x, L)))) per row, where the mask keeps the n_bins bins bin0, bin0+bin_step, ...
+ * (<= L/2) and zeroes the rest -- the spectral mask of modules/conv.py:24-29, fft_convolve(approx=slice),
+ * whose transform length is L = n_samples + atom_size (even; not a power of two in general, so this is a
+ * direct DFT over the kept bins).  The reference's band-limited correlation map is then the ordinary
+ * correlation (mpb200_correlate on a plan of L samples, first n_samples columns) of y with the atoms.
+ *   x (rows, n), y (rows, L). */
+int mpb200_band_limit(const float* x, int rows, int n, int L, int bin0, int bin_step, int n_bins, float* y,
+                      void* stream);
+
 /* out = irfft(keep bins [bin_lo, bin_hi) of rfft(x, norm="ortho"), n=n_out, norm="ortho") per row;
  * x is (rows, n_in), out (rows, n_out), both lengths powers of two >= 256 -- the band split of
  * modules/decompose.py:5-33 (fft_frequency_decompose) and the zero-stuffing resample of :36-73

@@ -30,12 +30,31 @@ def torch_conv(signal, atom):
     return _dense_map(signal, atom)
 
 
+def band_limited_map(signal2d: torch.Tensor, plan_long, n: int, slce: slice) -> torch.Tensor:
+    """modules/conv.py:24-29 with the engine's kernels: the product of the masked signal spectrum with the
+    atom spectra, inverted at length L = N + A, rolled and cropped (:51-53), equals the ordinary correlation
+    of y = irfft(mask(rfft(pad(signal, L)))) with the atoms, because t + i < L never wraps.  ``plan_long`` is
+    a plan for signals of L samples holding the atoms; returns (B, K, N)."""
+    y = engine.band_limit(signal2d, plan_long.n_samples, slce)
+    return plan_long.correlate(y)[..., :n].contiguous()
+
+
 def fft_convolve(signal, atoms, approx=None):
-    """modules/conv.py:11-53.  ``approx=None`` or ``int >= n_samples`` is the full product
-    (:48-49).  ``approx=slice`` (band-limited product over the bins of a length N+A transform,
-    :24-29) and ``approx=int < n_samples`` (:30-47, defective in the reference: only atom 0 is
-    populated) are not served by the engine."""
+    """modules/conv.py:11-53.  ``approx=None`` or ``int >= n_samples`` is the full product (:48-49);
+    ``approx=slice`` keeps only those rfft bins of the length N+A transform (:24-29).
+    ``approx=int < n_samples`` (:30-47) is defective in the reference (only atom 0 is populated,
+    SURVEY.md 8 a3) and is not served by the engine."""
     n = signal.shape[-1]
-    if isinstance(approx, slice) or (isinstance(approx, int) and not isinstance(approx, bool) and approx < n):
-        raise NotImplementedError("approx=slice / approx=int<N are not part of the engine yet")
+    if isinstance(approx, int) and not isinstance(approx, bool) and approx < n:
+        raise NotImplementedError("approx=int<N (top-k spectral bins, defective in the reference) is not part "
+                                  "of the engine")
+    if isinstance(approx, slice):
+        if atoms.dim() != 2:
+            raise ValueError("atoms must be (n_atoms, atom_size)")
+        b = signal.shape[0]
+        out_dev = signal.device
+        work = signal.device if signal.is_cuda else engine._require_cuda(None)
+        plan = get_plan(atoms.shape[0], atoms.shape[1], n + atoms.shape[1], b, work, "recorrelate")
+        plan.set_dictionary(atoms, normalize=False)
+        return band_limited_map(engine._dev_f32(signal, work, (b, n)), plan, n, approx).to(out_dev)
     return _dense_map(signal, atoms)

@@ -271,3 +271,125 @@ extern "C" int mpb200_spectral_band(const float* x, int rows, int n_in, float* o
     BF_CUDA(cudaFreeAsync(spec, st));
     return MPB200_OK;
 }
+
+// ---------------------------------------------------------------------------
+// mpb200_band_limit -- the spectral mask of modules/conv.py:24-29 (fft_convolve(approx=slice)):
+//     y = irfft( mask_bins( rfft( pad(x, L) ) ) ),   L even, arbitrary (N + atom_size in the reference)
+// as two direct DFT kernels over the kept bins only (an arithmetic progression bin0, bin0+step, ...):
+// the slice is usually a small band, and L = N + A is not a power of two.  The product with the
+// atom spectra of the reference is then the engine's ordinary correlation of y (t + i < L never wraps).
+// ---------------------------------------------------------------------------
+namespace mpb {
+
+// spec[row, jb] = sum_s x[row, s] * exp(-2 pi i * bin_jb * s / L).   grid = (n_bins, rows), 256 threads.
+__global__ void __launch_bounds__(256)
+k_band_forward(const float* __restrict__ x, int n, int L, int bin0, int bstep, const C32* __restrict__ twL,
+               C32* __restrict__ spec) {
+    const int jb = blockIdx.x, row = blockIdx.y, n_bins = gridDim.x;
+    const unsigned long long j = (unsigned long long)(bin0 + jb * bstep);
+    const float* __restrict__ xr = x + (size_t)row * n;
+    unsigned idx = (unsigned)((j * threadIdx.x) % (unsigned long long)L);
+    const unsigned inc = (unsigned)((j * 256ull) % (unsigned long long)L);
+    double re = 0.0, im = 0.0;
+    for (int s = threadIdx.x; s < n; s += 256) {
+        const C32 w = twL[idx];
+        const float v = xr[s];
+        re += (double)(v * w.x);
+        im -= (double)(v * w.y);
+        idx += inc;
+        if (idx >= (unsigned)L) idx -= (unsigned)L;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        re += __shfl_xor_sync(0xffffffffu, re, off);
+        im += __shfl_xor_sync(0xffffffffu, im, off);
+    }
+    __shared__ double s_re[8], s_im[8];
+    if ((threadIdx.x & 31) == 0) { s_re[threadIdx.x >> 5] = re; s_im[threadIdx.x >> 5] = im; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { re += s_re[w]; im += s_im[w]; }
+        spec[(size_t)row * n_bins + jb] = {(float)re, (float)im};
+    }
+}
+
+// y[row, t] = (1/L) sum_jb c_jb * Re( spec[row, jb] * exp(+2 pi i * bin_jb * t / L) ),  c = 1 for DC / Nyquist
+// (whose imaginary parts a C2R transform ignores), 2 otherwise.   grid = (ceil(L/256), rows), 256 threads.
+__global__ void __launch_bounds__(256)
+k_band_inverse(const C32* __restrict__ spec, int n_bins, int L, int bin0, int bstep, const C32* __restrict__ twL,
+               float* __restrict__ y) {
+    const int row = blockIdx.y;
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    __shared__ C32 s_spec[256];
+    const unsigned long long tt = (unsigned long long)(t < L ? t : 0);
+    unsigned idx = (unsigned)(((unsigned long long)bin0 * tt) % (unsigned long long)L);
+    const unsigned inc = (unsigned)(((unsigned long long)bstep * tt) % (unsigned long long)L);
+    float acc = 0.f, comp = 0.f;   // Kahan: up to L/2 terms of mixed sign
+    for (int base = 0; base < n_bins; base += 256) {
+        __syncthreads();
+        if (base + (int)threadIdx.x < n_bins) s_spec[threadIdx.x] = spec[(size_t)row * n_bins + base + threadIdx.x];
+        __syncthreads();
+        const int m = min(256, n_bins - base);
+        for (int i = 0; i < m; ++i) {
+            const int bin = bin0 + (base + i) * bstep;
+            const C32 w = twL[idx];
+            const C32 X = s_spec[i];
+            const bool edge = bin == 0 || 2 * bin == L;
+            const float term = edge ? X.x * w.x : 2.f * (X.x * w.x - X.y * w.y);
+            const float yk = term - comp;
+            const float sum = acc + yk;
+            comp = (sum - acc) - yk;
+            acc = sum;
+            idx += inc;
+            if (idx >= (unsigned)L) idx -= (unsigned)L;
+        }
+    }
+    if (t < L) y[(size_t)row * L + t] = acc / (float)L;
+}
+
+}  // namespace mpb
+
+extern "C" int mpb200_band_limit(const float* x, int rows, int n, int L, int bin0, int bin_step, int n_bins,
+                                 float* y, void* stream) {
+    using namespace mpb;
+    if (!x || !y || rows < 1 || n < 1 || L < n || n_bins < 0 || bin_step < 1 || bin0 < 0)
+        return fail(MPB200_EINVAL, "bad argument");
+    if (L % 2) return fail(MPB200_EINVAL, "mpb200_band_limit: the transform length must be even (the reference's "
+                                          "irfft returns L-1 samples for odd L)");
+    if (n_bins > 0 && bin0 + (long long)(n_bins - 1) * bin_step > L / 2)
+        return fail(MPB200_EINVAL, "bins beyond L/2");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_bins == 0) {
+        BF_CUDA(cudaMemsetAsync(y, 0, (size_t)rows * L * sizeof(float), st));
+        return MPB200_OK;
+    }
+    int dev = 0;
+    BF_CUDA(cudaGetDevice(&dev));
+    C32* twL = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_tab_mutex);
+        const long long key = (3LL << 40) + L;
+        auto it = g_tab.find({dev, key});
+        if (it != g_tab.end()) {
+            twL = it->second;
+        } else {
+            const long double two_pi = 6.283185307179586476925286766559005768L;
+            std::vector<C32> h((size_t)L);
+            for (int i = 0; i < L; ++i) {
+                long double a = two_pi * (long double)i / (long double)L;
+                h[i] = {(float)cosl(a), (float)sinl(a)};
+            }
+            int rc = upload(dev, key, h, &twL);
+            if (rc) return rc;
+        }
+    }
+    // spectrum scratch: stream-ordered allocation (freed on the same stream after the inverse kernel)
+    C32* spec = nullptr;
+    BF_CUDA(cudaMallocAsync((void**)&spec, (size_t)rows * n_bins * sizeof(C32), st));
+    k_band_forward<<<dim3(n_bins, rows), 256, 0, st>>>(x, n, L, bin0, bin_step, twL, spec);
+    BF_LAUNCH("k_band_forward");
+    k_band_inverse<<<dim3((L + 255) / 256, rows), 256, 0, st>>>(spec, n_bins, L, bin0, bin_step, twL, y);
+    BF_LAUNCH("k_band_inverse");
+    BF_CUDA(cudaFreeAsync(spec, st));
+    return MPB200_OK;
+}

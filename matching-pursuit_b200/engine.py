@@ -313,3 +313,21 @@ def subtract(residual: torch.Tensor, d_unit: torch.Tensor, winner: torch.Tensor)
         check(lib().mpb200_subtract(_ptr(residual), b, n, _ptr(d_unit), d_unit.shape[0], d_unit.shape[1],
                                     _ptr(winner), _stream_ptr(dev)), "mpb200_subtract")
     return residual
+
+
+def band_limit(x: torch.Tensor, length: int, slce: slice) -> torch.Tensor:
+    """``irfft(mask(rfft(pad(x, length))))`` per row of the CUDA tensor ``x`` (rows, n): the mask keeps the
+    rfft bins ``slce`` selects and zeroes the others -- the spectral mask of modules/conv.py:24-29.
+    ``length`` (= n_samples + atom_size there) must be even.  Returns (rows, length)."""
+    dev = _require_cuda(x.device)
+    x2 = _dev_f32(x, dev).reshape(-1, x.shape[-1])
+    n_bins_total = length // 2 + 1
+    if slce.step is not None and slce.step < 1:
+        raise ValueError("step must be greater than zero")      # what torch says of such a slice in the reference
+    bins = range(*slce.indices(n_bins_total))
+    out = torch.empty(x2.shape[0], length, device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        check(lib().mpb200_band_limit(_ptr(x2), x2.shape[0], x2.shape[1], length, bins[0] if len(bins) else 0,
+                                      bins.step if len(bins) else 1, len(bins), _ptr(out), _stream_ptr(dev)),
+              "mpb200_band_limit")
+    return out

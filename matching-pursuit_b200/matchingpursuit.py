@@ -223,10 +223,22 @@ def _run(signal: torch.Tensor, d: torch.Tensor, n_steps: int, device, approx, mo
     if plan is None:
         plan = get_plan(k, a, n, b, work, mode)
         plan.set_dictionary(d)
-    if isinstance(approx, slice) or (isinstance(approx, int) and not isinstance(approx, bool) and approx < n):
+    if isinstance(approx, int) and not isinstance(approx, bool) and approx < n:
         raise NotImplementedError(
-            "approx=slice / approx=int<N (band-limited or top-k-bin correlation, modules/conv.py:24-47) "
-            "is not part of the engine yet; pass approx=None or approx>=n_samples")
+            "approx=int<N (top-k spectral bins, modules/conv.py:30-47) is defective in the reference (only atom 0 "
+            "is populated) and is not part of the engine; pass approx=None, a slice, or approx>=n_samples")
+    if isinstance(approx, slice):
+        # band-limited correlation (modules/conv.py:24-29): the mask acts on the whole length-(N+A) spectrum of
+        # the residual, so every step changes the whole map -- the reference's recompute-per-step schedule it is
+        # (:278-280).  A caller-supplied compute_feature_map takes precedence, as there (:272-273).
+        from .conv import band_limited_map
+        dense_kwargs = dict(dense_kwargs) if dense_kwargs is not None else dict(
+            compute_feature_map=None, on_map=None, on_select=None, local_contrast_norm=False)
+        if dense_kwargs["compute_feature_map"] is None:
+            plan_long = get_plan(k, a, n + a, b, work, "recorrelate")
+            plan_long.set_dictionary(d)
+            dense_kwargs["compute_feature_map"] = \
+                lambda residual, du: band_limited_map(residual.view(b, n), plan_long, n, approx)
     if dense_kwargs is not None:
         atom, pos, val, residual, du = _pursuit_dense(sig2d, plan, n_steps, **dense_kwargs)
     else:
@@ -322,7 +334,8 @@ def sparse_code(signal, d, n_steps=100, device=None, approx=None, flatten=False,
     return flattened, scatter_segments                                       # :343-345
 
 
-def sparse_code_arrays(signal, d, n_steps=100, *, mode: str = "auto", plan: Optional[Plan] = None, device=None):
+def sparse_code_arrays(signal, d, n_steps=100, *, approx=None, mode: str = "auto", plan: Optional[Plan] = None,
+                       device=None):
     """Array-level form of :func:`sparse_code` for large batches: returns
     ``(atom int32 (B,S), pos int32 (B,S), val float32 (B,S), residual (B,1,N))``
     on ``signal.device`` without building B*S Python tuples."""
@@ -331,7 +344,7 @@ def sparse_code_arrays(signal, d, n_steps=100, *, mode: str = "auto", plan: Opti
     if _needs_grad(signal, d):
         raise MpbError("inputs require grad: the CUDA pursuit is forward-only")
     out_dev = signal.device
-    _, atom, pos, val, residual, _, _ = _run(signal, d, n_steps, device, None, mode, plan)
+    _, atom, pos, val, residual, _, _ = _run(signal, d, n_steps, device, approx, mode, plan)
     return atom.to(out_dev), pos.to(out_dev), val.to(out_dev), residual.view(batch, 1, n_samples).to(out_dev)
 
 

@@ -58,8 +58,46 @@ def test_golden_correlation_helpers():
     close(mconv.fft_convolve(sig, d, approx=200).cpu(), g["fft_full"], rel=1e-5)
     # atoms are used as given, not normalised
     close(mconv.torch_conv(sig, 3.0 * d).cpu(), 3.0 * g["torch_conv"], rel=1e-5)
+    # band-limited product over the bins of the length N+A transform (modules/conv.py:24-29)
+    close(mconv.fft_convolve(sig, d, approx=slice(3, 40)).cpu(), g["fft_slice"], rel=1e-5)
     with pytest.raises(NotImplementedError):
-        mconv.fft_convolve(sig, d, approx=slice(3, 40))
+        mconv.fft_convolve(sig, d, approx=17)       # defective in the reference
+
+
+@pytest.mark.parametrize("slce", [slice(3, 40), slice(None, None, 3), slice(-20, None), slice(0, None),
+                                  slice(7, 7)], ids=str)
+def test_band_limit_against_torch_fft(slce):
+    """mpb200_band_limit == irfft(mask(rfft(pad(x, L)))) for an even L that is not a power of two."""
+    torch.manual_seed(5)
+    n, a = 3000, 100
+    x = torch.randn(3, n)
+    spec = torch.fft.rfft(torch.nn.functional.pad(x.double(), (0, a)), dim=-1)
+    kept = torch.zeros_like(spec)
+    kept[..., slce] = spec[..., slce]
+    want = torch.fft.irfft(kept, n=n + a, dim=-1)
+    got = mpb.engine.band_limit(x.to(DEV), n + a, slce).cpu().double()
+    assert float((got - want).abs().max()) <= 2e-6 * max(1.0, float(want.abs().max()))
+    with pytest.raises(mpb.MpbError):
+        mpb.engine.band_limit(x.to(DEV), n + a + 1, slce)     # odd transform length
+    with pytest.raises(ValueError):
+        mpb.engine.band_limit(x.to(DEV), n + a, slice(100, 5, -2))    # torch rejects such a slice in the reference too
+
+
+def test_sparse_code_band_limited_against_oracle():
+    """sparse_code(approx=slice): the reference's per-step band-limited FFT correlation
+    (modules/matchingpursuit.py:278-280 -> modules/conv.py:24-29)."""
+    from parity import compare_with_oracle_trace
+    k, a, n, b, s = 24, 64, 2048, 2, 12
+    d = O.make_dictionary(k, a, seed=21)
+    sig = O.make_planted_signals(d, b, n, 8, seed=22)
+    slce = slice(0, 400)
+    tr = O.greedy_pursuit(sig, d, s, approx=slce, want_margin=True)
+    flat, scatter, residual = mpb.sparse_code(sig.to(DEV), d.to(DEV), s, approx=slce, flatten=True,
+                                              return_residual=True)
+    atom, pos, val = mpb.sparse_code_arrays(sig.to(DEV), d.to(DEV), s, approx=slce)[:3]
+    checked = compare_with_oracle_trace(tr, atom.cpu().numpy(), pos.cpu().numpy(), val.cpu().numpy(),
+                                        residual.cpu().numpy()[:, 0])
+    assert checked > 0
 
 
 def test_golden_band_split_and_merge():
