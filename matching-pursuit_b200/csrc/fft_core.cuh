@@ -167,13 +167,15 @@ struct Dft<4, DIR, T> {
 //    16 lanes of a half-warp walk j3 -> stride S (odd) -> 16 distinct 8-byte banks
 //  * pass-3 load: fixed j3, lanes walk mu = m1 + R1*m2 -> consecutive addresses
 //    inside one x, and the XS padding keeps consecutive x on distinct banks.
-template <int M_, typename Real>
+// E_ = 0: E = max(R1, 16); E_ = 32 halves the threads per transform (two butterflies per thread and pass).
+template <int M_, typename Real, int E_ = 0>
 struct BlockFft {
     using C = cpx<Real>;
     static constexpr int M = M_;
     static constexpr int R1 = M / 256;
     static_assert(R1 == 1 || R1 == 2 || R1 == 4 || R1 == 8 || R1 == 16 || R1 == 32, "M must be 256..8192, power of 2");
-    static constexpr int E = R1 > 16 ? R1 : 16;     // complex values per thread
+    static constexpr int E = E_ ? E_ : (R1 > 16 ? R1 : 16);     // complex values per thread
+    static_assert(E % 16 == 0 && E % R1 == 0, "E must be a multiple of 16 and of R1");
     static constexpr int T = M / E;                 // threads per transform
     static constexpr int NB1 = E / R1;              // pass-1 columns per thread
     static constexpr int NB2 = E / 16;              // pass-2 / pass-3 butterflies per thread

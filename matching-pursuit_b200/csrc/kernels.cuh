@@ -771,11 +771,22 @@ struct DeltaArgs {
 #ifndef MPB_DELTA_MINB
 #define MPB_DELTA_MINB 3
 #endif
+#ifndef MPB_DELTA_E
+#define MPB_DELTA_E 0          // complex values per thread of k_delta's transform (0: BlockFft's default, 16 up to 4096 points)
+#endif
+#ifndef MPB_DELTA_TPB
+#define MPB_DELTA_TPB 256      // minimum CTA size (several transforms share a CTA when one needs fewer threads)
+#endif
 template <int M2>
-__global__ void __launch_bounds__((BlockFft<M2, float>::T < 256 ? 256 : BlockFft<M2, float>::T), MPB_DELTA_MINB)
+struct DeltaCfg {
+    using F = BlockFft<M2, float, (MPB_DELTA_E && M2 / MPB_DELTA_E >= 32 && MPB_DELTA_E % (M2 / 256) == 0) ? MPB_DELTA_E : 0>;
+    static constexpr int TPB = F::T < MPB_DELTA_TPB ? MPB_DELTA_TPB : F::T;
+};
+template <int M2>
+__global__ void __launch_bounds__(DeltaCfg<M2>::TPB, MPB_DELTA_MINB)
 k_delta(const DeltaArgs a) {
-    using F = BlockFft<M2, float>;
-    constexpr int TPB = F::T < 256 ? 256 : F::T;
+    using F = typename DeltaCfg<M2>::F;
+    constexpr int TPB = DeltaCfg<M2>::TPB;
     constexpr int NT = TPB / F::T;
     constexpr int NW = F::T / 32;
     constexpr int RW0 = NW >= 4 ? NW - 2 : 0;            // first of the warps that re-derive the row maxima

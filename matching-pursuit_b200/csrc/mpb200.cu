@@ -291,8 +291,8 @@ static int step_refresh(Plan* p, int batch, cudaStream_t st) {
             d.row_val = p->row_val;
             d.row_pos = p->row_pos;
             MPB_DISPATCH_M(p->M2, {
-                using F = BlockFft<MM, float>;
-                constexpr int TPB = F::T < 256 ? 256 : F::T;
+                using F = typename DeltaCfg<MM>::F;
+                constexpr int TPB = DeltaCfg<MM>::TPB;
                 constexpr int NT = TPB / F::T;
                 const size_t smem = (size_t)(256 + NT * F::SMEM_CPX) * sizeof(C32) +
                                     (size_t)NT * 2 * d.cap * sizeof(float);
