@@ -58,6 +58,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (marks the run non-standard)")
     ap.add_argument("--iterations", type=int, default=0, help="override the iteration count (non-standard)")
     ap.add_argument("--mode", default="auto")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="c5 only: winner exchange fused into the pursuit over peer memory, or per-step NCCL all-gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU time of the cpu_baseline sample")
@@ -226,7 +228,9 @@ def run_atom_sharded(args):
     if args.iterations:
         s = args.iterations
     d, sig = make_inputs(torch, mpb, dev, batch, n, k, a, n_events=min(s, 1024), seed=1)   # same on every rank
-    pursuit = AtomShardedPursuit(k, a, n, batch, device=dev, mode=args.mode).set_dictionary(d)
+    pursuit = AtomShardedPursuit(k, a, n, batch, device=dev, mode=args.mode, exchange=args.exchange).set_dictionary(d)
+    nccl_ref = pursuit if (args.exchange == "nccl" or world == 1) else \
+        AtomShardedPursuit(k, a, n, batch, device=dev, mode="recorrelate", exchange="nccl").set_dictionary(d)
 
     def barrier():
         if world > 1:
@@ -248,9 +252,10 @@ def run_atom_sharded(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
-    # separate, un-timed pass with events around every exchange: per-step collective latency
-    pursuit.run(sig, min(s, 512), time_exchange=True)
-    ex = sorted(pursuit.exchange_ms)
+    # separate, un-timed pass with events around every exchange: per-step collective latency of the NCCL form
+    nccl_ref.run(sig, min(s, 512), time_exchange=True)
+    ex = sorted(nccl_ref.exchange_ms)
+    timed_out = pursuit.engine.plan.exchange_timed_out() if (args.exchange == "p2p" and world > 1) else False
     # all ranks must agree on the sequence
     if world > 1:
         chk = torch.stack([atom.double().sum(), pos.double().sum(), val.double().sum()])
@@ -267,12 +272,17 @@ def run_atom_sharded(args):
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic (planted atoms + noise, seeded)",
             "config": {"workload": desc, "iterations": s, "atoms_per_rank": (k + world - 1) // world, "mode": pursuit.engine.plan.mode,
-                       "parallelism": f"atom-sharded x{world}"},
+                       "parallelism": f"atom-sharded x{world}",
+                       "exchange": ("fused into k_apply: 8-byte-atomic stores into peer mailboxes over NVLink"
+                                    if (args.exchange == "p2p" and world > 1) else
+                                    "per-step NCCL all_gather_into_tensor between local_best and apply")},
+            "exchange_timed_out": timed_out,
             "gpu_launches": int(launches), "ranks_agree": agree,
             "exchange_latency_ms": {"mean": sum(ex) / max(len(ex), 1), "p50": ex[len(ex) // 2] if ex else None,
                                     "p99": ex[min(len(ex) - 1, int(0.99 * len(ex)))] if ex else None,
-                                    "what": "CUDA-event time around the per-step all_gather_into_tensor of "
-                                            "one 16-byte record per rank (0 at 1 GPU: no collective)"},
+                                    "what": "CUDA-event time around the per-step NCCL all_gather_into_tensor of "
+                                            "one 16-byte record per rank, measured on the NCCL form of the "
+                                            "exchange (0 at 1 GPU: no collective)"},
             "us_per_iteration": 1e3 * ms_total / args.steps / s,
         }), flush=True)
     if world > 1:

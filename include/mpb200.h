@@ -158,6 +158,24 @@ int mpb200_residual(mpb200_plan_t plan, float* residual_out, void* stream);
  * all-gather of mpb200_local_best records. */
 int mpb200_reduce_best(const mpb200_best* cand, int n_ranks, int batch, mpb200_best* winner, void* stream);
 
+/* Atom sharding with the exchange fused into the pursuit (no collective library in the loop).  Every rank
+ * creates a mailbox (2 x max_batch x world slots of 32 bytes, plain device memory) and the ranks trade the
+ * 64-byte CUDA IPC handles out of band (any transport: the Python layer uses one torch.distributed
+ * all-gather at set-up).  After mpb200_exchange_connect, mpb200_sparse_code works on the atom-sharded plan:
+ * in every iteration the kernel that applies the winner first writes this rank's candidate (value, atom,
+ * position, each in an 8-byte word with the iteration's sequence number) straight into every peer's mailbox
+ * over NVLink, polls its own mailbox for the `world` records of this iteration, and reduces them with the
+ * reference tie-break (max value, then lowest atom, then lowest position).  All ranks must issue the same
+ * calls in the same order.  A record that does not arrive within 20 s sets a flag (mpb200_exchange_status)
+ * instead of hanging.  No reference counterpart (the reference is single-device).
+ *   connect        handles = world x 64 bytes in rank order (this rank's own entry is ignored)
+ *   connect_local  same process, several plans (tests): mailboxes[r] = pointer from mpb200_exchange_mailbox */
+int mpb200_exchange_create(mpb200_plan_t plan, int world, int rank, unsigned char* handle_out /* 64 bytes or NULL */);
+int mpb200_exchange_connect(mpb200_plan_t plan, const unsigned char* handles);
+int mpb200_exchange_mailbox(mpb200_plan_t plan, void** mailbox);
+int mpb200_exchange_connect_local(mpb200_plan_t plan, void* const* mailboxes);
+int mpb200_exchange_status(mpb200_plan_t plan, int* timed_out);
+
 /* Selection on a DENSE map fm (batch, n_atoms, n_samples) that the caller
  * already holds (a `compute_feature_map` callback result, or
  * mpb200_correlate output handed to a per-step visitor): signed maximum per

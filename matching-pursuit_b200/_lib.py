@@ -92,6 +92,11 @@ _SIGNATURES = {
     "mpb200_gather_atoms": (_i, [_p, _p, _i, _i, _p, _p, _i, _p]),
     "mpb200_unit_norm": (_i, [_p, _p, _i, _i, C.c_float, _p]),
     "mpb200_fft_convolve": (_i, [_p, _p, _p, _i, _i, _i, _i, C.c_float, _p, _p]),
+    "mpb200_exchange_create": (_i, [_p, _i, _i, _p]),
+    "mpb200_exchange_connect": (_i, [_p, _p]),
+    "mpb200_exchange_mailbox": (_i, [_p, _p]),
+    "mpb200_exchange_connect_local": (_i, [_p, _p]),
+    "mpb200_exchange_status": (_i, [_p, _p]),
     "mpb200_band_limit": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "mpb200_spectral_band": (_i, [_p, _i, _i, _p, _i, _i, _i, _p]),
 }

@@ -48,6 +48,32 @@ __device__ __forceinline__ void warp_argmax(float& v, int& i) {
     }
 }
 
+// Rescan of one map row's block maxima outside the refreshed blocks [blk0, blk0 + nvb): folds this lane's
+// share into (v, at) = (value, position).  Long signals have thousands of blocks per row (4096 at 2^20
+// samples) and the winner's own row is rescanned in every iteration, so the loads are issued 16 deep per
+// lane and only the values are scanned; the position of the lane's best block is fetched once at the end.
+// Equal values resolve to the lowest block, i.e. the lowest position.
+__device__ __forceinline__ void rescan_row(const float* __restrict__ bm_val, const int* __restrict__ bm_pos, int NB,
+                                           int blk0, int nvb, int lane, float& v, int& at) {
+    float bv = -INFINITY;
+    int bi = -1;
+    for (int i0 = lane; i0 < NB; i0 += 32 * 16) {
+        float c[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int i = i0 + 32 * u;
+            c[u] = (i < NB && (i < blk0 || i >= blk0 + nvb)) ? bm_val[i] : -INFINITY;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+            if (c[u] > bv) {                              // ascending block index inside the lane
+                bv = c[u];
+                bi = i0 + 32 * u;
+            }
+    }
+    if (bi >= 0) take_better(v, at, bv, bm_pos[bi]);
+}
+
 // ---------------------------------------------------------------------------
 // y = x / (||x|| + eps) per row (modules/normalization.py:4-6). One warp per row.
 // ---------------------------------------------------------------------------
@@ -322,14 +348,7 @@ k_corr(const CorrArgs a) {
                     if (old_ok) {
                         if (lane == 31) take_better(v, at, old_v, old_p);   // nvb <= 22 < 32: lane 31 is free
                     } else {
-                        for (int i = lane; i < a.NB; i += 32) {
-                            if (i >= wi.blk0 && i < wi.blk0 + wi.nvb) continue;
-                            const float c = a.bm_val[o + i];
-                            if (c > v || (c == v && a.bm_pos[o + i] < at)) {
-                                v = c;
-                                at = a.bm_pos[o + i];
-                            }
-                        }
+                        rescan_row(a.bm_val + o, a.bm_pos + o, a.NB, wi.blk0, wi.nvb, lane, v, at);
                     }
                     warp_argmax(v, at);
                     if (lane == 0) {
@@ -467,7 +486,75 @@ struct ApplyArgs {
     GramUpdate* upd;      // (B)
     int* trunc_count;     // [2]: counter of this iteration at [step & 1]; the other one is reset here
     int parity;
+    // atom sharding over peer memory (SELECT only, world > 1): the local winner is written into every rank's
+    // mailbox and the global winner is reduced from the `world` records that arrive in ours.
+    MailSlot* const* peer_mail;   // [world] mailboxes, (2, mail_batch, world) slots each
+    int world, rank, mail_batch;
+    unsigned seq;                 // sequence number of this exchange (never 0)
+    int* xerr;                    // set when a record did not arrive in time
 };
+
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// All-to-all of one 12-byte candidate per rank and the reduction with the reference tie-break (max value,
+// then lowest atom, then lowest position), inside the kernel that applies the winner: the transfer is `world`
+// 8-byte-atomic stores per word over NVLink and a poll of the local mailbox.  Called by a whole CTA.
+__device__ __forceinline__ Best exchange_best(const ApplyArgs& a, int b, Best mine, Best* s_slot) {
+    const unsigned long long tag = (unsigned long long)a.seq << 32;
+    const size_t slot0 = ((size_t)(a.seq & 1u) * a.mail_batch + b) * a.world;
+    if ((int)threadIdx.x < a.world) {
+        MailSlot* dst = a.peer_mail[threadIdx.x] + slot0 + a.rank;
+        st_sys_u64(&dst->w[0], tag | (unsigned)__float_as_int(mine.value));
+        st_sys_u64(&dst->w[1], tag | (unsigned)mine.atom);
+        st_sys_u64(&dst->w[2], tag | (unsigned)mine.position);
+        // collect rank threadIdx.x's record from the local mailbox
+        const MailSlot* src = a.peer_mail[a.rank] + slot0 + threadIdx.x;
+        unsigned long long w0, w1, w2;
+        const unsigned long long t0 = global_ns();
+        bool ok = true;
+        for (;;) {
+            w0 = ld_sys_u64(&src->w[0]);
+            w1 = ld_sys_u64(&src->w[1]);
+            w2 = ld_sys_u64(&src->w[2]);
+            if ((unsigned)(w0 >> 32) == a.seq && (unsigned)(w1 >> 32) == a.seq && (unsigned)(w2 >> 32) == a.seq) break;
+            if (*reinterpret_cast<volatile int*>(a.xerr) != 0 || global_ns() - t0 > 20000000000ull) {   // 20 s
+                ok = false;
+                break;
+            }
+        }
+        Best r;
+        if (ok) {
+            r.value = __int_as_float((int)(unsigned)w0);
+            r.atom = (int)(unsigned)w1;
+            r.position = (int)(unsigned)w2;
+        } else {
+            *a.xerr = 1;
+            r = mine;
+        }
+        r.pad = 0;
+        s_slot[threadIdx.x] = r;
+    }
+    __syncthreads();
+    Best w = s_slot[0];
+    for (int r = 1; r < a.world; ++r) {
+        const Best c = s_slot[r];
+        if (c.value > w.value || (c.value == w.value && (c.atom < w.atom || (c.atom == w.atom && c.position < w.position))))
+            w = c;
+    }
+    return w;
+}
 
 template <int M, bool SELECT>
 __global__ void __launch_bounds__(256)
@@ -482,6 +569,10 @@ k_apply(const ApplyArgs a) {
     Best w;
     if constexpr (SELECT) {
         w = block_best(a.row_val, a.row_pos, b, a.nloc, a.atom_lo, &s_best);
+        if (a.world > 1) {
+            __shared__ Best s_slot[64];
+            w = exchange_best(a, b, w, s_slot);
+        }
     } else {
         w = a.winner[b];
     }
@@ -1003,15 +1094,7 @@ k_delta(const DeltaArgs a) {
             if (old_ok) {
                 if (lane == 31) take_better(v, at, old_v[wi], old_p[wi]);   // nvb <= 30: lane 31 is free
             } else {
-                for (int i = lane; i < a.NB; i += 32) {
-                    if (i >= blk0 && i < blk0 + nvb) continue;
-                    const float c = a.bm_val[o + i];
-                    const int cp = a.bm_pos[o + i];
-                    if (c > v || (c == v && cp < at)) {
-                        v = c;
-                        at = cp;
-                    }
-                }
+                rescan_row(a.bm_val + o, a.bm_pos + o, a.NB, blk0, nvb, lane, v, at);
             }
             warp_argmax(v, at);
             if (lane == 0) {

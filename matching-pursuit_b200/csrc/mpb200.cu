@@ -99,6 +99,7 @@ static int dev_alloc(Plan* p, T** ptr, size_t count) {
 }
 
 static void free_plan(Plan* p) {
+    for (void* m : p->ipc_opened) cudaIpcCloseMemHandle(m);
     for (void* e : p->ev_pool) cudaEventDestroy((cudaEvent_t)e);
     for (void* q : p->allocs) cudaFree(q);
     if (p->h_stage) cudaFreeHost(p->h_stage);
@@ -234,6 +235,16 @@ static int launch_apply(Plan* p, int batch, const Best* winner, int step, int n_
     a.winspec = p->winspec;
     a.do_fft = do_fft;
     a.gram = p->mode == MPB200_MODE_GRAM || p->mode == MPB200_MODE_SGRAM;
+    a.world = 1;
+    if (SELECT && p->xconnected && p->xworld > 1) {
+        a.peer_mail = p->peer_mail;
+        a.world = p->xworld;
+        a.rank = p->xrank;
+        a.mail_batch = p->Bmax;
+        a.seq = ++p->xseq;
+        if (p->xseq == 0xffffffffu) p->xseq = 0;     // 0 is the "empty" tag of a fresh mailbox
+        a.xerr = p->xerr;
+    }
     a.upd = p->upd;
     a.trunc_count = p->trunc_count;
     a.parity = (int)(p->iter & 1u);
@@ -419,6 +430,39 @@ static int build_sgram_tables(Plan* p, cudaStream_t st) {
     return launch_window_fft_ex(p->M2, p->tw1b, p->tw2, p->dict, p->A, p->A, p->win_atoms, p->K, p->atomspec, st);
 }
 
+// With CUDA's lazy module loading the FIRST use of a kernel may synchronise the context.  A pursuit whose
+// kernels wait for other ranks must never meet such a load while a waiting kernel is resident, so every
+// kernel the plan can launch is loaded up front.
+template <typename K>
+static void touch(K kernel) {
+    cudaFuncAttributes at;
+    if (cudaFuncGetAttributes(&at, kernel) != cudaSuccess) cudaGetLastError();
+}
+static int preload_kernels(Plan* p) {
+    MPB_DISPATCH_M(p->M, {
+        touch(k_apply<MM, true>);
+        touch(k_apply<MM, false>);
+        touch(k_window_fft<MM>);
+        touch(k_corr<MM, MODE_BLOCKMAX>);
+        touch(k_corr<MM, MODE_DENSE>);
+        touch(k_corr<MM, MODE_DENSE | MODE_BLOCKMAX>);
+        touch(k_corr<MM, MODE_BLOCKMAX | MODE_ROWMAX>);
+        touch(k_corr<MM, MODE_DENSE | MODE_BLOCKMAX | MODE_ROWMAX>);
+    });
+    if (p->mode == MPB200_MODE_SGRAM) {
+        MPB_DISPATCH_M(p->M2, { touch(k_delta<MM>); });
+    }
+    touch(k_gram_update<16>);
+    touch(k_gram_update<32>);
+    touch(k_gram_update<64>);
+    touch(k_gram_update<128>);
+    touch(k_gram_update<256>);
+    touch(k_rowmax);
+    touch(k_local_best);
+    touch(k_reduce_best);
+    return MPB200_OK;
+}
+
 static int check_plan(Plan* p, bool need_dict) {
     if (!p) return fail(MPB200_EINVAL, "null plan");
     if (need_dict && !p->dict_set) return fail(MPB200_ESTATE, "mpb200_plan_set_dictionary has not been called");
@@ -510,10 +554,10 @@ int mpb200_plan_create(mpb200_plan_t* out, int n_atoms, int atom_size, int n_sam
         const bool fits = gram_bytes <= budget && gram_bytes + map_bytes <= (uint64_t)(0.8 * (double)free_b);
         if (fits && (long long)max_batch * 16 >= n_atoms && nvb_max <= 32) mode = MPB200_MODE_GRAM;
         // SGRAM pays off once its persistent grid reaches a steady state (tens of (pair, signal) work items
-        // per CTA: measured 46 vs 63 us per atom-step at 32 x 2048 items, but 166 vs 132 us at 1 x 1024);
+        // per CTA: measured 46 vs 63 us per atom-step at 32 x 2048 items, 268 vs 341 us at 1 x 8192, 60 vs 63 us at 1 x 1024);
         // below that the one-transform-per-CTA re-correlation kernel has the shorter critical path.
         else if (sgram_ok && (cap >= max_batch || cap >= 32) &&
-                 (long long)(cap < max_batch ? cap : max_batch) * p->npairs >= 16384)
+                 (long long)(cap < max_batch ? cap : max_batch) * p->npairs >= 4096)
             mode = MPB200_MODE_SGRAM;
         else mode = MPB200_MODE_RECORRELATE;
     }
@@ -846,9 +890,12 @@ int mpb200_sparse_code(mpb200_plan_t plan, const float* signal, int batch, int n
     if (n_steps > 0 && (!atom_out || !pos_out || !val_out)) return fail(MPB200_EINVAL, "null output");
     if (batch < 1 || batch > p->Bmax) return fail(MPB200_EINVAL, "batch must be in [1, max_batch]");
     if (!signal) return fail(MPB200_EINVAL, "null signal");
-    if (p->lo != 0 || p->hi != p->K)
-        return fail(MPB200_ESTATE, "mpb200_sparse_code needs a plan that owns every atom; "
-                                   "sharded plans use begin/local_best/apply");
+    const bool sharded = p->lo != 0 || p->hi != p->K;
+    if (sharded && !(p->xconnected && p->xworld > 1))
+        return fail(MPB200_ESTATE, "mpb200_sparse_code on an atom-sharded plan needs a connected exchange "
+                                   "(mpb200_exchange_create/connect); otherwise use begin/local_best/apply");
+    if (p->xconnected && p->xworld > 1 && batch > p->Bcap)
+        return fail(MPB200_EINVAL, "atom-sharded pursuit: the batch must fit the resident capacity of every rank");
     cudaStream_t st = (cudaStream_t)stream;
     // signals are independent problems: the map modes walk the batch in balanced resident sub-batches
     const int n_sub = (batch + p->Bcap - 1) / p->Bcap;
@@ -862,6 +909,95 @@ int mpb200_sparse_code(mpb200_plan_t plan, const float* signal, int batch, int n
                              val_out ? val_out + eo : nullptr, st);
         if (rc) return rc;
     }
+    return MPB200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// atom-sharded exchange over peer memory
+// ---------------------------------------------------------------------------
+int mpb200_exchange_create(mpb200_plan_t plan, int world, int rank, unsigned char* handle_out) {
+    Plan* p = reinterpret_cast<Plan*>(plan);
+    int rc = check_plan(p, false);
+    if (rc) return rc;
+    if (world < 1 || world > 64 || rank < 0 || rank >= world) return fail(MPB200_EINVAL, "bad world/rank (world <= 64)");
+    if (p->mail) return fail(MPB200_ESTATE, "the plan already has a mailbox");
+    const size_t slots = (size_t)2 * p->Bmax * world;
+    // plain cudaMalloc (not a pool): the allocation is exported through CUDA IPC
+    rc = dev_alloc(p, &p->mail, slots);
+    if (!rc) rc = dev_alloc(p, &p->peer_mail, (size_t)world);
+    if (!rc) rc = dev_alloc(p, &p->xerr, (size_t)1);
+    if (rc) return rc;
+    MPB_CUDA(cudaMemset(p->mail, 0, slots * sizeof(MailSlot)));
+    MPB_CUDA(cudaMemset(p->xerr, 0, sizeof(int)));
+    rc = preload_kernels(p);
+    if (rc) return rc;
+    p->xworld = world;
+    p->xrank = rank;
+    p->xseq = 0;
+    if (handle_out) {
+        cudaIpcMemHandle_t h;
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+        MPB_CUDA(cudaIpcGetMemHandle(&h, p->mail));
+        memcpy(handle_out, &h, 64);
+    }
+    return MPB200_OK;
+}
+
+static int finish_connect(Plan* p, const std::vector<MailSlot*>& ptrs) {
+    MPB_CUDA(cudaMemcpy(p->peer_mail, ptrs.data(), ptrs.size() * sizeof(MailSlot*), cudaMemcpyHostToDevice));
+    p->xconnected = true;
+    return MPB200_OK;
+}
+
+int mpb200_exchange_connect(mpb200_plan_t plan, const unsigned char* handles) {
+    Plan* p = reinterpret_cast<Plan*>(plan);
+    int rc = check_plan(p, false);
+    if (rc) return rc;
+    if (!p->mail || !handles) return fail(MPB200_ESTATE, "mpb200_exchange_create has not been called");
+    std::vector<MailSlot*> ptrs((size_t)p->xworld, nullptr);
+    for (int r = 0; r < p->xworld; ++r) {
+        if (r == p->xrank) { ptrs[(size_t)r] = p->mail; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * 64, 64);
+        void* q = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(MPB200_ECUDA, std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(r) + "): " +
+                                          cudaGetErrorString(e));
+        }
+        p->ipc_opened.push_back(q);
+        ptrs[(size_t)r] = reinterpret_cast<MailSlot*>(q);
+    }
+    return finish_connect(p, ptrs);
+}
+
+int mpb200_exchange_mailbox(mpb200_plan_t plan, void** mailbox) {
+    Plan* p = reinterpret_cast<Plan*>(plan);
+    if (!p || !mailbox) return fail(MPB200_EINVAL, "null argument");
+    if (!p->mail) return fail(MPB200_ESTATE, "mpb200_exchange_create has not been called");
+    *mailbox = p->mail;
+    return MPB200_OK;
+}
+
+int mpb200_exchange_connect_local(mpb200_plan_t plan, void* const* mailboxes) {
+    Plan* p = reinterpret_cast<Plan*>(plan);
+    int rc = check_plan(p, false);
+    if (rc) return rc;
+    if (!p->mail || !mailboxes) return fail(MPB200_ESTATE, "mpb200_exchange_create has not been called");
+    std::vector<MailSlot*> ptrs((size_t)p->xworld, nullptr);
+    for (int r = 0; r < p->xworld; ++r) ptrs[(size_t)r] = reinterpret_cast<MailSlot*>(mailboxes[r]);
+    if (ptrs[(size_t)p->xrank] != p->mail) return fail(MPB200_EINVAL, "mailboxes[rank] must be this plan's own mailbox");
+    return finish_connect(p, ptrs);
+}
+
+int mpb200_exchange_status(mpb200_plan_t plan, int* timed_out) {
+    Plan* p = reinterpret_cast<Plan*>(plan);
+    int rc = check_plan(p, false);
+    if (rc) return rc;
+    if (!timed_out) return fail(MPB200_EINVAL, "null argument");
+    *timed_out = 0;
+    if (p->xerr) MPB_CUDA(cudaMemcpy(timed_out, p->xerr, sizeof(int), cudaMemcpyDeviceToHost));
     return MPB200_OK;
 }
 

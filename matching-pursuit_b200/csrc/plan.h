@@ -55,6 +55,15 @@ struct Plan {
     unsigned iter = 0;              // iterations applied since begin (parity selects trunc_count slot)
     int refresh_every = 0;          // GRAM: full re-correlation every this many iterations (0 = never)
 
+    // atom-sharded exchange over peer memory (NVLink): every rank owns a mailbox that all ranks write into
+    int xworld = 1, xrank = 0;
+    MailSlot* mail = nullptr;               // local mailbox: [2 parities][Bmax][world]
+    MailSlot** peer_mail = nullptr;         // device array [world]: every rank's mailbox as seen from this device
+    std::vector<void*> ipc_opened;          // peer mappings to close
+    int* xerr = nullptr;                    // device flag: an exchange timed out
+    unsigned xseq = 0;                      // exchanges issued so far (sequence number of the next one is xseq + 1)
+    bool xconnected = false;
+
     // staging for the host-buffer entry point
     float* d_signal = nullptr;
     int32_t *d_atom = nullptr, *d_pos = nullptr;

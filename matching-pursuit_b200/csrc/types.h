@@ -20,6 +20,13 @@ struct GramUpdate {   // one per signal and iteration (GRAM mode)
     int valid;     // 1: apply the Gram update; 0: this signal takes the FFT route
 };
 
+// One rank's candidate for one signal in another rank's mailbox (atom-sharded exchange over peer memory).
+// Every 8-byte word carries (payload, sequence number), so a word is either entirely old or entirely new
+// (8-byte stores are single-copy atomic): no fence and no separate flag, as in NCCL's LL protocol.
+struct MailSlot {
+    unsigned long long w[4];   // [0] value bits | seq << 32, [1] atom | seq << 32, [2] position | seq << 32, [3] unused
+};
+
 struct Best {  // == mpb200_best
     float value;
     int atom;

@@ -95,7 +95,14 @@ class AtomShardedPursuit:
     """
 
     def __init__(self, n_atoms: int, atom_size: int, n_samples: int, batch: int, group=None, engine=None,
-                 device=None, mode: str = "auto"):
+                 device=None, mode: str = "auto", exchange: str = "nccl"):
+        """``exchange``: ``"nccl"`` -- per-step ``all_gather_into_tensor`` of the 16-byte records between
+        ``local_best`` and ``apply`` (host-driven loop); ``"p2p"`` -- the exchange is fused into the kernel
+        that applies the winner (peer-memory stores over NVLink into every rank's mailbox, include/mpb200.h
+        ``mpb200_exchange_*``): the whole pursuit is one library call with no collective in the loop."""
+        if exchange not in ("nccl", "p2p"):
+            raise ValueError("exchange must be 'nccl' or 'p2p'")
+        self.exchange = exchange
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -104,6 +111,14 @@ class AtomShardedPursuit:
         self.engine = engine if engine is not None else PlanEngine(n_atoms, atom_size, n_samples, batch,
                                                                    self.lo, self.hi, device=device, mode=mode)
         self.exchange_ms: List[float] = []
+        if exchange == "p2p" and self.world > 1:
+            plan = self.engine.plan
+            mine = plan.exchange_create(self.world, self.rank)
+            local = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(plan.device)
+            every = torch.empty(self.world * 64, dtype=torch.uint8, device=plan.device)
+            dist.all_gather_into_tensor(every, local, group=self.group)      # set-up only: trade the IPC handles
+            plan.exchange_connect(bytes(every.cpu().numpy().tobytes()))
+            dist.barrier(group=self.group)
 
     def set_dictionary(self, d: torch.Tensor) -> "AtomShardedPursuit":
         self.engine.set_dictionary(d)
@@ -120,6 +135,9 @@ class AtomShardedPursuit:
     def run(self, signal: torch.Tensor, n_steps: int, time_exchange: bool = False):
         """Returns ``(atom int32 (B,S), pos int32 (B,S), val float32 (B,S), residual (B,N))``."""
         eng = self.engine
+        if self.exchange == "p2p" and self.world > 1:
+            atom, pos, val, res = eng.plan.sparse_code(signal, n_steps, want_residual=True)
+            return atom, pos, val, res
         eng.begin(signal)
         b = signal.shape[0]
         wins = []

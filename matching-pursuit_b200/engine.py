@@ -195,6 +195,37 @@ class Plan:
         with torch.cuda.device(self.device):
             check(self._lib.mpb200_apply(self._h, _ptr(winner), _stream_ptr(self.device)), "mpb200_apply")
 
+    # ---- atom-sharded exchange over peer memory --------------------------
+    def exchange_create(self, world: int, rank: int) -> bytes:
+        """Allocate this rank's mailbox; returns its 64-byte CUDA IPC handle for the peers."""
+        buf = (C.c_ubyte * 64)()
+        with torch.cuda.device(self.device):
+            check(self._lib.mpb200_exchange_create(self._h, world, rank, buf), "mpb200_exchange_create")
+        return bytes(buf)
+
+    def exchange_connect(self, handles: bytes) -> None:
+        """``handles``: the ``world`` IPC handles in rank order (64 bytes each), other processes' mailboxes."""
+        buf = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
+        with torch.cuda.device(self.device):
+            check(self._lib.mpb200_exchange_connect(self._h, buf), "mpb200_exchange_connect")
+
+    def exchange_mailbox(self) -> int:
+        out = C.c_void_p()
+        check(self._lib.mpb200_exchange_mailbox(self._h, C.byref(out)), "mpb200_exchange_mailbox")
+        return out.value
+
+    def exchange_connect_local(self, mailboxes) -> None:
+        """Same-process form (several plans in one process): ``mailboxes[r]`` from :meth:`exchange_mailbox`."""
+        arr = (C.c_void_p * len(mailboxes))(*mailboxes)
+        with torch.cuda.device(self.device):
+            check(self._lib.mpb200_exchange_connect_local(self._h, arr), "mpb200_exchange_connect_local")
+
+    def exchange_timed_out(self) -> bool:
+        flag = C.c_int(0)
+        with torch.cuda.device(self.device):
+            check(self._lib.mpb200_exchange_status(self._h, C.byref(flag)), "mpb200_exchange_status")
+        return bool(flag.value)
+
     def residual(self) -> torch.Tensor:
         out = torch.empty(self.batch, self.n_samples, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.device):

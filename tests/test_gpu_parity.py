@@ -240,6 +240,43 @@ def test_atom_sharded_stepwise_equals_oracle():
                   np.stack(atoms), np.stack(poss), np.stack(vals), res)
 
 
+@pytest.mark.parametrize("mode", ["recorrelate", "sgram"])
+def test_atom_sharded_fused_exchange_equals_oracle(mode):
+    """The exchange fused into the pursuit (mailboxes in peer memory, mpb200_exchange_*), exercised in one
+    process: three atom-sharded plans on three streams of one GPU trade their candidates through each
+    other's mailboxes; every plan must report the oracle's sequence and the same residual."""
+    k, a, n, b, s = 37, 128, 4096, 3, 24
+    d = O.make_dictionary(k, a, seed=5)
+    sig = O.make_planted_signals(d, b, n, 12, seed=6).to(DEV)
+    tr = O.greedy_pursuit(sig.cpu(), d, s, want_margin=True)
+    bounds = [0, 11, 24, 37]
+    world = len(bounds) - 1
+    plans = [mpb.Plan(k, a, n, b, device=DEV, mode=mode, atom_range=(lo, hi)).set_dictionary(d)
+             for lo, hi in zip(bounds[:-1], bounds[1:])]
+    with pytest.raises(mpb.MpbError):
+        plans[0].sparse_code(sig, s)                 # sharded plan without a connected exchange
+    for r, p in enumerate(plans):
+        assert len(p.exchange_create(world, r)) == 64
+    boxes = [p.exchange_mailbox() for p in plans]
+    for p in plans:
+        p.exchange_connect_local(boxes)
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(device=DEV) for _ in plans]
+    outs = []
+    for rep in range(2):                              # twice: sequence numbers keep counting across calls
+        outs = []
+        for p, st in zip(plans, streams):
+            with torch.cuda.stream(st):
+                outs.append(p.sparse_code(sig, s))
+        torch.cuda.synchronize()
+    assert not any(p.exchange_timed_out() for p in plans)
+    atom, pos, val, res = (t.cpu().numpy() for t in outs[0])
+    for o in outs[1:]:
+        for x, y in zip(outs[0], o):
+            assert torch.equal(x, y)
+    assert compare_with_oracle_trace(tr, atom, pos, val, res) > 0
+
+
 # --------------------------------------------------------------------------
 # drop-in return conventions
 # --------------------------------------------------------------------------
