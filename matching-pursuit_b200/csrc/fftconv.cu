@@ -149,10 +149,12 @@ static int launch_rows(const BfGeom& g, const BfTables& t, BfRowsArgs a, cudaStr
         constexpr int TPB = F::T < 128 ? 128 : F::T;
         constexpr int NT = TPB / F::T;
         const size_t smem = (size_t)(256 + NT * F::SMEM_CPX) * sizeof(C32);
-        static bool once = false;
-        if (!once) {
+        static bool once[64] = {false};           // the attribute is per device
+        int dev_ = 0;
+        BF_CUDA(cudaGetDevice(&dev_));
+        if (dev_ < 0 || dev_ >= 64 || !once[dev_]) {
             BF_CUDA(cudaFuncSetAttribute(k_bf_rows<MM, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            once = true;
+            if (dev_ >= 0 && dev_ < 64) once[dev_] = true;
         }
         k_bf_rows<MM, DIR><<<(a.n_transforms + NT - 1) / NT, TPB, smem, st>>>(a);
     });

@@ -6,6 +6,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -48,9 +50,23 @@ int fail(int code, const std::string& msg) {
         default: return fail(MPB200_EINVAL, "unsupported FFT size");      \
     }
 
+// Opt a kernel in to `bytes` of dynamic shared memory.  The attribute is per device and per kernel, so the
+// largest size granted so far is remembered per (device, kernel address); plans on several devices of one
+// process, or plans with different staging sizes, each get what they need.
 template <typename K>
 static cudaError_t allow_smem(K kernel, size_t bytes) {
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> granted;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const std::pair<int, const void*> key(dev, reinterpret_cast<const void*>(kernel));
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = granted.find(key);
+    if (it != granted.end() && it->second >= bytes) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) granted[key] = bytes;
+    return e;
 }
 
 // ---------------------------------------------------------------------------
@@ -115,8 +131,7 @@ static int launch_window_fft_ex(int M, const C32* tw1, const C32* tw2, const flo
     MPB_DISPATCH_M(M, {
         using F = BlockFft<MM, float>;
         const size_t smem = (size_t)(F::SMEM_CPX + 256) * sizeof(C32);
-        static bool once = false;
-        if (!once) { MPB_CUDA(allow_smem(k_window_fft<MM>, smem)); once = true; }
+        MPB_CUDA(allow_smem(k_window_fft<MM>, smem));
         k_window_fft<MM><<<nwin, F::T, smem, st>>>(src, row_stride, row_len, win, tw1, tw2, winspec);
     });
     MPB_LAUNCH_CHECK("k_window_fft");
@@ -138,8 +153,7 @@ static int launch_corr(Plan* p, CorrArgs a, int groups, cudaStream_t st) {
         constexpr int NT = TPB / F::T;
         size_t smem = (size_t)(256 + NT * F::SMEM_CPX) * sizeof(C32);
         if (MPB_CORR_SEP && (MODE & MODE_ROWMAX) != 0) smem += (size_t)NT * (p->bm_cap + 64) * sizeof(float2);
-        static size_t allowed = 0;
-        if (smem > allowed) { MPB_CUDA(allow_smem(k_corr<MM, MODE>, smem)); allowed = smem; }
+        MPB_CUDA(allow_smem(k_corr<MM, MODE>, smem));
         dim3 grid((a.npairs + NT - 1) / NT, groups);
         k_corr<MM, MODE><<<grid, TPB, smem, st>>>(a);
     });
@@ -251,8 +265,7 @@ static int launch_apply(Plan* p, int batch, const Best* winner, int step, int n_
     MPB_DISPATCH_M(p->M, {
         using F = BlockFft<MM, float>;
         const size_t smem = (size_t)(F::SMEM_CPX + 256) * sizeof(C32);
-        static bool once = false;
-        if (!once) { MPB_CUDA((allow_smem(k_apply<MM, SELECT>, smem))); once = true; }
+        MPB_CUDA((allow_smem(k_apply<MM, SELECT>, smem)));
         k_apply<MM, SELECT><<<batch, 256, smem, st>>>(a);
     });
     MPB_LAUNCH_CHECK("k_apply");
@@ -307,8 +320,7 @@ static int step_refresh(Plan* p, int batch, cudaStream_t st) {
                 constexpr int NT = TPB / F::T;
                 const size_t smem = (size_t)(256 + NT * F::SMEM_CPX) * sizeof(C32) +
                                     (size_t)NT * 2 * d.cap * sizeof(float);
-                static size_t allowed = 0;
-                if (smem > allowed) { MPB_CUDA(allow_smem(k_delta<MM>, smem)); allowed = smem; }
+                MPB_CUDA(allow_smem(k_delta<MM>, smem));
                 if (p->delta_occ == 0) {
                     MPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->delta_occ, k_delta<MM>, TPB, smem));
                     if (p->delta_occ < 1) p->delta_occ = 1;
@@ -407,8 +419,7 @@ static int build_pair_spectra(Plan* p, cudaStream_t st) {
     MPB_DISPATCH_M(p->M, {
         using F = BlockFft<MM, double>;
         const size_t smem = (size_t)(F::SMEM_CPX + 256) * sizeof(cpx<double>);
-        static bool once = false;
-        if (!once) { MPB_CUDA((allow_smem(k_pair_spectra<MM, double>, smem))); once = true; }
+        MPB_CUDA((allow_smem(k_pair_spectra<MM, double>, smem)));
         k_pair_spectra<MM, double><<<p->npairs, F::T, smem, st>>>(p->dict, p->A, p->lo, p->hi, p->tw1d, p->tw2d,
                                                                    p->pairspec);
     });
@@ -421,8 +432,7 @@ static int build_sgram_tables(Plan* p, cudaStream_t st) {
     MPB_DISPATCH_M(p->M2, {
         using F = BlockFft<MM, double>;
         const size_t smem = (size_t)(F::SMEM_CPX + 256) * sizeof(cpx<double>);
-        static bool once = false;
-        if (!once) { MPB_CUDA((allow_smem(k_pair_spectra<MM, double>, smem))); once = true; }
+        MPB_CUDA((allow_smem(k_pair_spectra<MM, double>, smem)));
         k_pair_spectra<MM, double><<<p->npairs, F::T, smem, st>>>(p->dict, p->A, p->lo, p->hi, p->tw1bd, p->tw2d,
                                                                    p->pairspec2);
     });
