@@ -102,6 +102,8 @@ CASES = [
     (8, 1024, 8192, 2, 16, "planted"),      # M = 4096
     (6, 2048, 16384, 1, 12, "planted"),     # M = 8192
     (5, 700, 700, 2, 8, "noise"),           # atom as long as the signal
+    (9, 33, 1001, 2, 20, "noise"),          # odd everything: map rows padded for the bulk copies (SGRAM)
+    (3, 2, 67, 3, 10, "noise"),             # tiny atoms, prime signal length
 ]
 
 
