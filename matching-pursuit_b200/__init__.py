@@ -20,7 +20,7 @@ from .engine import Plan, reduce_best, unpack_best, unit_norm, gather_atoms, sca
 from .matchingpursuit import (sparse_code, sparse_code_arrays, sparse_feature_map, build_scatter_segments,  # noqa: F401
                               flatten_atom_dict, dictionary_learning_step, get_plan, clear_plan_cache, EventList)
 
-from . import conv, decompose, distributed, fft, mp, multibanddict, sparse  # noqa: F401,E402
+from . import autograd, conv, decompose, distributed, fft, mp, multibanddict, sparse  # noqa: F401,E402
 from .multibanddict import BandSpec, MultibandDictionaryLearning  # noqa: F401,E402
 from .sparse import sparsify2  # noqa: F401,E402
 

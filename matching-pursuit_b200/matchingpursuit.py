@@ -264,7 +264,7 @@ def sparse_code(signal, d, n_steps=100, device=None, approx=None, flatten=False,
                                   "(modules/matchingpursuit.py:50); only (B,1,N) is supported")
     if _needs_grad(signal, d):
         raise MpbError("inputs require grad: the CUDA pursuit is forward-only; run under torch.no_grad() "
-                       "or use matching_pursuit_b200.autograd for the differentiable re-evaluation")
+                       "or use matching_pursuit_b200.autograd.sparse_code_differentiable for the differentiable re-evaluation")
     n_samples = time
     n_atoms, atom_size = d.shape[0], d.shape[-1]
     out_dev = signal.device

@@ -196,3 +196,43 @@ def test_multiband_config4_shapes():
     for s in sizes:
         r, _, _ = specs[sizes.index(s)].recon(split[s], steps)
         assert float((split[s] - r).norm()) < float(split[s].norm())
+
+
+def test_differentiable_reevaluation_matches_reference_gradients():
+    """Gradients of a loss on (values, residual) with respect to the dictionary and the signal: the CUDA pursuit
+    + PyTorch re-evaluation on fixed indices against the reference's dense loop restated with CPU autograd
+    (modules/matchingpursuit.py:269-328: conv1d map, torch.max over the flattened map, scatter, subtract)."""
+    import torch.nn.functional as F
+    torch.manual_seed(3)
+    k, a, n, b, s = 12, 32, 512, 2, 10
+    d0 = torch.zeros(k, a).uniform_(-1, 1)
+    sig0 = O.make_planted_signals(O.unit_norm(d0), b, n, 6, seed=9)
+
+    def reference_loss(sig, d):
+        du = d / (torch.norm(d, dim=-1, keepdim=True) + 1e-8)
+        residual, vals, seq = sig.clone(), [], []
+        for _ in range(s):
+            fm = F.conv1d(F.pad(residual, (0, a)), du.view(k, 1, a))[..., :n]
+            value, index = torch.max(fm.reshape(b, -1), dim=-1)
+            atom, pos = index // n, index % n
+            sparse = torch.zeros(b, 1, n + a)
+            for j in range(b):
+                sparse[j, 0, pos[j]: pos[j] + a] = du[atom[j]] * value[j]
+            residual = residual - sparse[..., :n]
+            vals.append(value)
+            seq.append((atom.clone(), pos.clone()))
+        return (residual ** 2).sum() + torch.stack(vals).sum(), seq
+
+    sig_r, d_r = sig0.clone().requires_grad_(True), d0.clone().requires_grad_(True)
+    loss_r, seq = reference_loss(sig_r, d_r)
+    loss_r.backward()
+
+    sig_g, d_g = sig0.clone().to(DEV).requires_grad_(True), d0.clone().to(DEV).requires_grad_(True)
+    atom, pos, val, residual = mpb.autograd.sparse_code_differentiable(sig_g, d_g, s)
+    for step, (ra, rp) in enumerate(seq):
+        assert torch.equal(atom[:, step].cpu(), ra) and torch.equal(pos[:, step].cpu(), rp)
+    loss_g = (residual ** 2).sum() + val.sum()
+    loss_g.backward()
+    assert abs(float(loss_g.detach()) - float(loss_r.detach())) <= 1e-4 * abs(float(loss_r.detach()))
+    close(d_g.grad.cpu(), d_r.grad, rel=1e-3)
+    close(sig_g.grad.cpu(), sig_r.grad, rel=1e-3)
