@@ -673,6 +673,8 @@ k_gram_update(const GramArgs a) {
     const int b = row / a.nloc, j = row - b * a.nloc;
     const GramUpdate u = a.upd[b];
     if (!u.valid) return;
+    const float old_v = a.row_val[row];      // needed at the very end: requested now
+    const int old_p = a.row_pos[row];
     const int p = u.position;
     const float nv = -u.value;
     const int first = max(0, p - a.A + 1), last = min(a.N - 1, p + a.A - 1);
@@ -757,28 +759,18 @@ k_gram_update(const GramArgs a) {
             }
         }
     }
-    // row maximum over all NB blocks: refreshed ones from registers, the rest from the table
-    float v = -INFINITY;
-    int bi_best = INT_MAX;
-    for (int q = 0; q * 32 < a.NB; ++q) {
-        const int bi = q * 32 + lane;
-        const int src = bi - blk0;
-        const bool fresh = src >= 0 && src < nvb;
-        const float fv = __shfl_sync(0xffffffffu, my_v, fresh ? src : 0);
-        float c = -INFINITY;
-        if (bi < a.NB) c = fresh ? fv : a.bm_val[bm0 + bi];
-        if (c > v) {
-            v = c;
-            bi_best = bi;
-        }
-    }
-    warp_argmax(v, bi_best);
-    const int src = bi_best - blk0;
-    const bool fresh = bi_best != INT_MAX && src >= 0 && src < nvb;
-    const int fp = __shfl_sync(0xffffffffu, my_p, fresh ? src : 0);
+    // row maximum: the refreshed blocks sit in registers (lane i < nvb holds block blk0 + i).  If the old row
+    // maximum lies outside the window it is still valid and only has to be compared with them; otherwise
+    // the row's other block maxima are rescanned (16 loads in flight per lane, rescan_row).
+    const int old_b = old_p / BLK;
+    float v = lane < nvb ? my_v : -INFINITY;
+    int at = lane < nvb ? my_p : INT_MAX;
+    if (old_b >= blk0 && old_b < blk0 + nvb) rescan_row(a.bm_val + bm0, a.bm_pos + bm0, a.NB, blk0, nvb, lane, v, at);
+    else if (lane == 0) take_better(v, at, old_v, old_p);
+    warp_argmax(v, at);
     if (lane == 0) {
         a.row_val[row] = v;
-        a.row_pos[row] = (bi_best == INT_MAX) ? 0 : (fresh ? fp : a.bm_pos[bm0 + bi_best]);
+        a.row_pos[row] = (at == INT_MAX) ? 0 : at;
     }
 }
 
