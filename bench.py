@@ -38,6 +38,11 @@ WORKLOADS = {
            "BASELINE configs[1]: batch 64 x 2^15 samples, 512-atom x 1024 dictionary, 256 iterations"),
     "c1": (1, 2 ** 15, 512, 512, 32,
            "BASELINE configs[0]: 1 x 2^15 samples, 512 atoms x 512 samples, 32 iterations"),
+    # multi-band codec (6 independent per-band pursuits around an FFT band split): handled by run_multiband()
+    "c4": (16, 2 ** 16, 1024, 128, 64,
+           "BASELINE configs[3]: multi-band dictionary (modules/multibanddict.py), 6 bands (2048..65536 samples) x "
+           "1024 atoms x 128 samples, per-band MP on 2^16-sample signals; batch 16 and 64 iterations per band "
+           "(experiments/e_2024_4_24/experiment.py:28-40)"),
     # atom-sharded (not batch-sharded): handled by run_atom_sharded()
     "c5": (1, 2 ** 20, 16384, 2048, 2048,
            "BASELINE configs[4]: single 2^20-sample signal, 16384-atom x 2048 dictionary, 2048 iterations, "
@@ -208,6 +213,105 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------
+# multi-band workload (configs[3])
+# --------------------------------------------------------------------------
+def run_multiband(args):
+    """6 band dictionaries, FFT band split on the device, one pursuit per band.  `value` times the split and
+    the six array-level pursuits with device-resident inputs; `e2e` times MultibandDictionaryLearning.encode --
+    the call a user of modules/multibanddict.py makes (:399-404) -- with HOST signals in and the reference's
+    per-event tuples out.  Batches shard across ranks without communication."""
+    import torch
+    import torch.distributed as dist
+    import matching_pursuit_b200 as mpb
+    from matching_pursuit_b200 import decompose as mdec
+    from oracle import mp_oracle as O
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    batch, n, k, a, s, desc = WORKLOADS["c4"]
+    if args.batch:
+        batch = args.batch
+    if args.iterations:
+        s = args.iterations
+    sizes = [2048 * 2 ** i for i in range(6)]
+    specs = [mpb.BandSpec(sz, k, a, device=dev, signal_samples=n, is_lowest_band=(i == 0)) for i, sz in enumerate(sizes)]
+    for i, spec in enumerate(specs):
+        spec.d = O.make_dictionary(k, a, seed=10 + i).to(dev)
+    model = mpb.MultibandDictionaryLearning(specs, n_samples=n)
+    # family-P signals: planted atoms of a length-128 dictionary plus noise (SURVEY.md 8d)
+    x_host = O.make_planted_signals(O.make_dictionary(k, a, seed=0), batch, n, 4 * s, seed=1 + rank).pin_memory()
+    x = x_host.to(dev)
+
+    def device_pass():
+        split = mdec.fft_frequency_decompose(x, sizes[0])
+        return [mpb.sparse_code_arrays(split[sz], spec.d, s) for sz, spec in zip(sizes, specs)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        device_pass()
+    barrier()
+    launches0 = mpb.lib().mpb200_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = device_pass()
+    e1.record()
+    barrier()
+    launches = mpb.lib().mpb200_launch_count() - launches0
+    model.encode(x_host, s)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        enc = model.encode(x_host, s)
+    torch.cuda.synchronize()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    t = torch.tensor([e0.elapsed_time(e1), wall_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    atoms = batch * s * len(sizes) * world
+    if rank == 0:
+        modes = sorted({mpb.matchingpursuit.get_plan(k, a, sz, batch, dev, "auto").mode for sz in sizes})
+        line = {
+            "metric": "MP atoms/sec (6 bands x 1024x128 dict, 2^16 sig)", "value": atoms * args.steps / (float(t[0]) / 1e3),
+            "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": float(t[0]) / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic (planted atoms + noise, seeded)",
+            "config": {"workload": desc, "batch_per_gpu": batch, "iterations_per_band": s, "band_sizes": sizes,
+                       "modes": modes, "parallelism": f"batch-sharded x{world}, no collective"},
+            "gpu_launches": int(launches),
+            "e2e": {"value": atoms * args.steps / (float(t[1]) / 1e3), "unit": UNIT,
+                    "h2d_bytes_per_step": batch * n * 4 * world,
+                    "d2h_bytes_per_step": int(sum(len(enc[sz][0]) for sz in sizes)) * (a * 4 + 24) * world,
+                    "api": "MultibandDictionaryLearning.encode (host signals in, reference event tuples out)"},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            torch.set_num_threads(os.cpu_count() or 1)
+            ob = O.MultibandOracle([O.BandOracle(sz, O.make_dictionary(k, a, seed=10 + i), is_lowest_band=(i == 0))
+                                    for i, sz in enumerate(sizes)], n)
+            xs, cs = x_host[:1], max(2, s // 16)
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                ob.encode(xs, cs)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": cs * len(sizes) / dt, "unit": UNIT, "cores": os.cpu_count() or 1,
+                                    "kind": "port", "sample": f"1 signal, {cs} iterations per band, all 6 bands, "
+                                                              f"{round(dt, 2)} s"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------
 # atom-sharded workload (configs[4])
 # --------------------------------------------------------------------------
 def run_atom_sharded(args):
@@ -309,6 +413,9 @@ def main():
         return
     if args.workload == "c5":
         run_atom_sharded(args)
+        return
+    if args.workload == "c4":
+        run_multiband(args)
         return
     import torch
     import torch.distributed as dist

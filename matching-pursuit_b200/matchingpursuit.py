@@ -33,21 +33,33 @@ from .engine import Plan
 # new dictionary, which the reference allows to change on every call.
 # --------------------------------------------------------------------------
 _PLAN_CACHE: "dict[tuple, Plan]" = {}
-_PLAN_CACHE_MAX = 4
+_PLAN_CACHE_MAX = 8              # e.g. the six bands of a multi-band codec stay resident
+_PLAN_CACHE_FRACTION = 0.25      # of the device memory: older plans are closed before a new one is sized
+
+
+def _evict_until(dev_index: int, max_bytes: int, max_entries: int) -> None:
+    def held():
+        return sum(p.device_bytes for key, p in _PLAN_CACHE.items() if key[0] == dev_index)
+    while _PLAN_CACHE and (len(_PLAN_CACHE) > max_entries or held() > max_bytes):
+        _PLAN_CACHE.pop(next(iter(_PLAN_CACHE))).close()          # oldest first (dicts keep insertion order)
 
 
 def get_plan(n_atoms: int, atom_size: int, n_samples: int, batch: int, device, mode: str = "auto") -> Plan:
     dev = engine._require_cuda(device)
     key = (dev.index, n_atoms, atom_size, n_samples, mode)
-    plan = _PLAN_CACHE.get(key)
-    if plan is None or plan.max_batch < batch:
-        if plan is not None:
-            plan.close()
-            del _PLAN_CACHE[key]
-        while len(_PLAN_CACHE) >= _PLAN_CACHE_MAX:
-            _PLAN_CACHE.pop(next(iter(_PLAN_CACHE))).close()
-        plan = Plan(n_atoms, atom_size, n_samples, batch, mode=mode, device=dev)
-        _PLAN_CACHE[key] = plan
+    plan = _PLAN_CACHE.pop(key, None)
+    if plan is not None and plan.max_batch < batch:
+        plan.close()
+        plan = None
+    if plan is None:
+        total = torch.cuda.get_device_properties(dev).total_memory
+        _evict_until(dev.index, int(_PLAN_CACHE_FRACTION * total), _PLAN_CACHE_MAX - 1)
+        try:
+            plan = Plan(n_atoms, atom_size, n_samples, batch, mode=mode, device=dev)
+        except MpbError:
+            clear_plan_cache()                                    # make room and try once more
+            plan = Plan(n_atoms, atom_size, n_samples, batch, mode=mode, device=dev)
+    _PLAN_CACHE[key] = plan                                       # (re)inserted last: most recently used
     return plan
 
 
