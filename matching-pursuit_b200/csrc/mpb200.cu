@@ -171,6 +171,17 @@ static int corr_groups(const Plan* p, int nwin) {
     return g;
 }
 
+// Grid depth of the FFT route inside the map modes (winners that overhang the right edge): usually no window
+// at all, so the launch is kept just deep enough to fill the chip twice instead of eight times.
+static int trunc_groups(const Plan* p, int nwin) {
+    const int tpb_pairs = (p->M >= 4096) ? 1 : (4096 / p->M > 8 ? 8 : 4096 / p->M);
+    const int gx = (p->npairs + tpb_pairs - 1) / tpb_pairs;
+    int g = (p->sm_count * 2 + gx - 1) / gx;
+    if (g < 1) g = 1;
+    if (g > nwin) g = nwin;
+    return g;
+}
+
 static CorrArgs base_corr_args(const Plan* p) {
     CorrArgs a;
     memset(&a, 0, sizeof(a));
@@ -341,7 +352,7 @@ static int step_refresh(Plan* p, int batch, cudaStream_t st) {
             a.dense_row_stride = (long long)p->nloc * p->NS;
             a.dense_atom_stride = p->NS;
             a.dense_col_off = 0;
-            rc = launch_corr<MODE_DENSE | MODE_BLOCKMAX | MODE_ROWMAX>(p, a, corr_groups(p, batch), st);
+            rc = launch_corr<MODE_DENSE | MODE_BLOCKMAX | MODE_ROWMAX>(p, a, trunc_groups(p, batch), st);
         }
     } else if (p->mode == MPB200_MODE_GRAM) {
         const bool refresh = p->refresh_every > 0 && (p->iter + 1) % (unsigned)p->refresh_every == 0;
@@ -382,7 +393,7 @@ static int step_refresh(Plan* p, int batch, cudaStream_t st) {
             a.dense_row_stride = (long long)p->nloc * p->N;
             a.dense_atom_stride = p->N;
             a.dense_col_off = 0;
-            rc = launch_corr<MODE_DENSE | MODE_BLOCKMAX | MODE_ROWMAX>(p, a, corr_groups(p, batch), st);
+            rc = launch_corr<MODE_DENSE | MODE_BLOCKMAX | MODE_ROWMAX>(p, a, trunc_groups(p, batch), st);
         }
     } else {
         CorrArgs a = base_corr_args(p);
