@@ -56,6 +56,6 @@ class MatchingPursuit(nn.Module):
             step = channels[:, i, :]                                          # strided view: scatter into a copy
             buf = torch.zeros(batch, n, device=work)
             engine.scatter_rows(buf, scaled, rows, p)
-            residual = residual - buf                                         # mp.py:64
+            engine.scatter_rows(residual, engine.gather_atoms(atoms, k, -(v * v)), rows, p)   # mp.py:64: r - v^2*atom
             step.copy_(buf)                                                   # mp.py:65
         return channels.to(out_dev)
