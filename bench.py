@@ -148,6 +148,17 @@ def make_inputs(torch, mpb, dev, batch, n, k, a, n_events, seed):
 # --------------------------------------------------------------------------
 # CPU baseline (oracle port of the reference path)
 # --------------------------------------------------------------------------
+def cpu_model() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.lower().startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_atoms_per_second(torch, n, k, a, budget_s, seed=1):
     """Times the CPU oracle (a port of modules/matchingpursuit.py::sparse_code,
     same torch kernels as the reference) on ONE signal of the workload, with
@@ -207,7 +218,8 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "cpu_model": cpu_model(), "torch_threads": torch.get_num_threads()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -604,7 +616,8 @@ def main():
         line["roofline"] = roofline
     if not args.no_cpu_baseline and world == 1:
         v, cores, sample, detail = cpu_atoms_per_second(torch, n, k, a, args.cpu_seconds)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                                "cpu_model": cpu_model(), "torch_threads": torch.get_num_threads()}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
