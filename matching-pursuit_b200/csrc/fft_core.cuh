@@ -157,6 +157,16 @@ struct Dft<4, DIR, T> {
     }
 };
 
+// k = hi + (k - hi) with hi the largest power of two < k (k/2 when k is a power of two): both parts are < k.
+template <int K, int P = 1, bool DONE = (2 * P >= K)>
+struct SplitPoint {
+    static constexpr int value = SplitPoint<K, 2 * P>::value;
+};
+template <int K, int P>
+struct SplitPoint<K, P, true> {
+    static constexpr int value = P;
+};
+
 // Three-pass block FFT of M = 256*R1 points carried by T = M/E threads, each
 // holding E = max(R1,16) complex values in registers.
 //
@@ -215,6 +225,40 @@ struct BlockFft {
                     v = cmul(v, w);
                 }
                 sm[addr(m1, x, j3)] = v;
+            });
+        });
+    }
+
+    // z^1 .. z^(P-1) from z: every power is the product of two earlier ones (z^(2^k + j) = z^(2^k) * z^j), so
+    // P-2 complex multiplications, at most log2(P) deep -- the rounding error stays at a few ulp.
+    template <int P>
+    static MPB_HD void powers(C z, C* zp) {
+        zp[1] = z;
+        static_for<2, P>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            constexpr int hi = SplitPoint<k>::value;
+            zp[k] = cmul(zp[hi], zp[k - hi]);
+        });
+    }
+
+    // pass 1 with the twiddles w^(c*m1) generated from the one table entry w^c: trades R1-1 table loads per
+    // column (L1/L2 traffic on the busiest unit of k_delta) for R1-2 complex multiplications.
+    template <int DIR>
+    static MPB_HD void pass1_gen(C* r, int tl, C* sm, const C* __restrict__ tw1) {
+        static_assert(R1 >= 4, "generated twiddles need a radix >= 4 first pass");
+        static_for<0, NB1>([&](auto uc) {
+            constexpr int u = decltype(uc)::value;
+            const int c = tl + T * u;
+            Dft<R1, DIR, Real>::run(r + u * R1);
+            const int x = c >> 4, j3 = c & 15;
+            C z = tw1[256 + c];
+            if constexpr (DIR < 0) z.y = -z.y;
+            C zp[R1];
+            powers<R1>(z, zp);
+            sm[addr(0, x, j3)] = r[u * R1];
+            static_for<1, R1>([&](auto m1c) {
+                constexpr int m1 = decltype(m1c)::value;
+                sm[addr(m1, x, j3)] = cmul(r[u * R1 + m1], zp[m1]);
             });
         });
     }
