@@ -479,6 +479,7 @@ struct ApplyArgs {
     const float* dict;    // whole unit dictionary (K, A)
     float* residual;      // (B, N)
     int nloc, atom_lo, A, N, blk_shift, NB;
+    int n_atoms;          // atoms of the whole dictionary
     int step, n_steps;
     int* atom_out;        // (B, n_steps) or null
     int* pos_out;
@@ -585,6 +586,10 @@ k_apply(const ApplyArgs a) {
     } else {
         w = a.winner[b];
     }
+    // memory safety whatever the map holds (NaN/Inf inputs can leave a row without a valid maximum, and a
+    // sharded caller may hand in anything): the winner is forced into the dictionary and into the signal
+    w.atom = min(max(w.atom, 0), a.n_atoms - 1);
+    w.position = min(max(w.position, 0), a.N - 1);
     const int p = w.position;
     if (threadIdx.x == 0 && a.atom_out) {
         a.atom_out[(size_t)b * a.n_steps + a.step] = w.atom;
@@ -1060,6 +1065,7 @@ k_delta(const DeltaArgs a) {
                                     fmaxf(fmaxf(c1.x, c1.y), fmaxf(c1.z, c1.w)));
                     const int kmax = __reduce_max_sync(0xffffffffu, float_key(v));
                     v = __int_as_float(kmax ^ ((kmax >> 31) & 0x7fffffff));
+                    if (!(v == v)) v = -INFINITY;                 // a NaN in the map never wins (as in the comparison-based paths)
                     int at = INT_MAX;                             // descending order: the lowest matching position survives
                     at = (c1.w + 0.0f == v) ? 131 : at;
                     at = (c1.z + 0.0f == v) ? 130 : at;

@@ -245,6 +245,7 @@ static int launch_apply(Plan* p, int batch, const Best* winner, int step, int n_
     a.residual = p->residual;
     a.nloc = p->nloc;
     a.atom_lo = p->lo;
+    a.n_atoms = p->K;
     a.A = p->A;
     a.N = p->N;
     a.blk_shift = p->blk_shift;

@@ -456,6 +456,23 @@ def test_headline_shape_schedules_agree():
     np.testing.assert_allclose((out.cpu() + sr).numpy(), sig.view(b, n).cpu().numpy(), atol=5e-5)
 
 
+@pytest.mark.parametrize("mode", ["recorrelate", "gram", "sgram", "full"])
+def test_non_finite_input_is_memory_safe(mode):
+    """NaN / Inf samples make the reference's result meaningless (torch.max returns NaN); the engine promises
+    only that nothing is read or written out of bounds: events stay inside the dictionary and the signal, the
+    launch sequence completes, and an untouched second signal is coded exactly as it is alone."""
+    k, a, n, b, s = 16, 64, 2048, 2, 12
+    d = O.make_dictionary(k, a, seed=1)
+    sig = O.make_planted_signals(d, b, n, 6, seed=2)
+    bad = sig.clone()
+    bad[0, 0, 100] = float("nan")
+    bad[0, 0, 900] = float("inf")
+    atom, pos, val, res = run_plan(bad, d, s, mode)
+    assert ((atom >= 0) & (atom < k)).all() and ((pos >= 0) & (pos < n)).all()
+    ref = run_plan(sig[1:], d, s, mode)
+    assert np.array_equal(atom[1:], ref[0]) and np.array_equal(pos[1:], ref[1]) and np.array_equal(val[1:], ref[2])
+
+
 def test_errors():
     with pytest.raises(mpb.MpbError):
         mpb.Plan(4, 5000, 128, 1, device=DEV)            # window FFT longer than supported
