@@ -575,11 +575,12 @@ int mpb200_plan_create(mpb200_plan_t* out, int n_atoms, int atom_size, int n_sam
         const uint64_t budget = gram_budget_bytes ? gram_budget_bytes : (uint64_t)(0.4 * (double)free_b);
         const bool fits = gram_bytes <= budget && gram_bytes + map_bytes <= (uint64_t)(0.8 * (double)free_b);
         if (fits && (long long)max_batch * 16 >= n_atoms && nvb_max <= 32) mode = MPB200_MODE_GRAM;
-        // SGRAM pays off once its persistent grid reaches a steady state (tens of (pair, signal) work items
-        // per CTA: measured 46 vs 63 us per atom-step at 32 x 2048 items, 268 vs 341 us at 1 x 8192, 60 vs 63 us at 1 x 1024);
-        // below that the one-transform-per-CTA re-correlation kernel has the shorter critical path.
+        // SGRAM against windowed re-correlation, measured: 46 vs 63 us per atom-step at 32 x 2048 (pair, signal)
+        // work items, 268 vs 341 us at 1 x 8192, 58.5 vs 62.7 us per iteration at 1 x 1024 (one rank of configs[4]
+        // on 8 GPUs).  Below about a thousand items the persistent grid is mostly empty and the resident map
+        // (and its longer first pass) buys nothing.
         else if (sgram_ok && (cap >= max_batch || cap >= 32) &&
-                 (long long)(cap < max_batch ? cap : max_batch) * p->npairs >= 4096)
+                 (long long)(cap < max_batch ? cap : max_batch) * p->npairs >= 1024)
             mode = MPB200_MODE_SGRAM;
         else mode = MPB200_MODE_RECORRELATE;
     }

@@ -187,6 +187,7 @@ def test_auto_mode_resolution():
     assert mpb.Plan(512, 1024, 2 ** 15, 64, device=DEV).mode == "gram"          # BASELINE configs[1]
     assert mpb.Plan(512, 512, 2 ** 15, 1, device=DEV).mode == "recorrelate"     # too few work items for the map modes
     assert mpb.Plan(4096, 2048, 2 ** 15, 32, device=DEV).mode == "sgram"
+    assert mpb.Plan(16384, 2048, 2 ** 20, 1, device=DEV, atom_range=(0, 2048)).mode == "sgram"   # one rank of configs[4]
     p = mpb.Plan(4096, 2048, 2 ** 15, 1024, device=DEV)                          # BASELINE configs[2]: 275 GB table
     assert p.mode == "sgram" and 32 <= p.resident_batch < 1024
     p.close()
