@@ -80,3 +80,40 @@ def test_pair_packing_identity():
     want1 = np.array([np.dot(x[t:t + a], d1) for t in range(valid)])
     np.testing.assert_allclose(y.real[:valid], want0, atol=1e-9)
     np.testing.assert_allclose(y.imag[:valid], want1, atol=1e-9)
+
+
+def test_synthesised_gram_row_identity():
+    """SGRAM never stores the K^2(2A-1) cross-correlation table: for a winner atom k* and an atom pair (d0, d1),
+        G[k*, d0, l] + i G[k*, d1, l] = IFFT_M2( FFT([0^(A-1), d_k*]) * E )[l + A - 1],   |l| < A,   M2 >= 2A,
+    with E the pair spectrum of the identity above at length M2, and subtracting v * d_k* at position p changes
+    the correlation map of atom d by exactly -v * G[k*, d, t - p] wherever the atom fits inside the signal."""
+    rng = np.random.default_rng(1)
+    a, m2, n = 48, 128, 400
+    dk, d0, d1 = (rng.standard_normal(a) for _ in range(3))
+    s = np.fft.fft(np.concatenate([np.zeros(a - 1), dk, np.zeros(m2 - 2 * a + 1)]))
+    z = np.zeros(m2, dtype=complex)
+    z[:a] = d0 + 1j * d1
+    y = np.fft.ifft(s * np.fft.ifft(z)) * m2
+
+    def gram(d, lag):                                   # sum_i d_k*[i + lag] d[i]
+        return sum(dk[i + lag] * d[i] for i in range(a) if 0 <= i + lag < a)
+
+    lags = range(-(a - 1), a)
+    np.testing.assert_allclose([y.real[l + a - 1] for l in lags], [gram(d0, l) for l in lags], atol=1e-9)
+    np.testing.assert_allclose([y.imag[l + a - 1] for l in lags], [gram(d1, l) for l in lags], atol=1e-9)
+    # the map update it stands for
+    r = rng.standard_normal(n)
+    p, v = 123, 0.7
+
+    def corr(sig, d):
+        pad = np.concatenate([sig, np.zeros(a)])
+        return np.array([np.dot(pad[t:t + a], d) for t in range(n)])
+
+    r2 = r.copy()
+    r2[p:p + a] -= v * dk
+    delta = corr(r2, d0) - corr(r, d0)
+    want = np.zeros(n)
+    for l in lags:
+        if 0 <= p + l < n:
+            want[p + l] = -v * gram(d0, -l)             # map[t] = sum_i r[t+i] d[i]; t = p + l' sees d_k*[i - l']
+    np.testing.assert_allclose(delta, want, atol=1e-9)
