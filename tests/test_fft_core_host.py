@@ -115,5 +115,5 @@ def test_synthesised_gram_row_identity():
     want = np.zeros(n)
     for l in lags:
         if 0 <= p + l < n:
-            want[p + l] = -v * gram(d0, -l)             # map[t] = sum_i r[t+i] d[i]; t = p + l' sees d_k*[i - l']
+            want[p + l] = -v * gram(d0, l)              # map[t] = sum_i r[t+i] d[i], and r changed by -v d_k*[t+i-p]
     np.testing.assert_allclose(delta, want, atol=1e-9)
