@@ -127,6 +127,30 @@ def test_oracle_parity(case, mode):
     assert checked > 0
 
 
+def _fuzz_shapes():
+    rng = np.random.default_rng(20261018)
+    shapes = [(1, 1, 5, 1, 3), (1, 2, 2, 2, 2), (2, 3, 3, 1, 4), (3, 1, 64, 2, 6)]      # degenerate corners first
+    for _ in range(28):
+        a = int(rng.choice([2, 3, 5, 17, 31, 64, 100, 129, 255, 300]))
+        n = int(rng.integers(a, 12 * a + 40))
+        shapes.append((int(rng.integers(1, 41)), a, n, int(rng.integers(1, 5)), int(rng.integers(3, 16))))
+    return shapes
+
+
+@pytest.mark.parametrize("shape", _fuzz_shapes(), ids=lambda s: "K%d_A%d_N%d_B%d_S%d" % s)
+def test_random_shapes_all_schedules_against_oracle(shape):
+    """Seeded random shapes (single atoms, atoms of 1-3 samples, atoms as long as the signal, odd sizes) through
+    all four schedules against the oracle; noise signals, so near-ties and truncated winners are common."""
+    k, a, n, b, s = shape
+    d = O.make_dictionary(k, a, seed=k * 131 + a)
+    sig = O.make_noise_signals(b, n, seed=n * 7 + b)
+    tr = O.greedy_pursuit(sig, d, s, want_margin=True)
+    for mode in ("recorrelate", "full", "gram", "sgram"):
+        atom, pos, val, res = run_plan(sig, d, s, mode)
+        assert ((atom >= 0) & (atom < k)).all() and ((pos >= 0) & (pos < n)).all(), mode
+        compare_with_oracle_trace(tr, atom, pos, val, res)
+
+
 @pytest.mark.parametrize("refresh", [0, 50])
 def test_gram_mode_long_run_against_oracle(refresh):
     """Incremental Gram updates over 300 iterations (drift check), with and without periodic
