@@ -106,7 +106,11 @@ int mpb200_plan_timing_read(mpb200_plan_t plan, double* ms_by_tag, int64_t* coun
  * x / (||x||_2 + 1e-8) per row -- modules/normalization.py:4-6, applied by the
  * reference at every entry (modules/matchingpursuit.py:254) -- and derives the
  * atom-pair spectra (and the Gram table in GRAM mode).  The caller's buffer is
- * not modified and may be freed once `stream` has passed this call. */
+ * not modified and may be freed once `stream` has passed this call.  A
+ * fingerprint of `d` is compared ON THE DEVICE with the previous call's: when
+ * the bits are unchanged the table-building kernels return at once, so callers
+ * that keep the reference's habit of passing the dictionary with every call
+ * do not pay for it, and nothing synchronises with the host. */
 int mpb200_plan_set_dictionary(mpb200_plan_t plan, const float* d, void* stream);
 /* Same without the normalisation: the atoms are used as given -- what the
  * correlation helpers modules/conv.py:4-9 (torch_conv) and :11-53 (fft_convolve)

@@ -85,7 +85,29 @@ __device__ __forceinline__ void rescan_row(const float* __restrict__ bm_val, con
 // ---------------------------------------------------------------------------
 // y = x / (||x|| + eps) per row (modules/normalization.py:4-6). One warp per row.
 // ---------------------------------------------------------------------------
-__global__ void k_unit_norm(const float* __restrict__ x, float* __restrict__ y, int rows, int cols, float eps) {
+// Dictionary fingerprint: position-weighted 64-bit sum of the float bits.  set_dictionary compares it on the
+// device with the previous one and the table-building kernels below return at once when nothing changed
+// (`skip`): the reference re-derives everything from `d` on every call (modules/matchingpursuit.py:254), and
+// callers that pass an unchanged dictionary again should not pay for it -- without a host synchronisation.
+__global__ void k_fingerprint(const float* __restrict__ d, size_t n, unsigned long long* __restrict__ acc) {
+    unsigned long long s = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        s += (unsigned long long)(unsigned)__float_as_int(d[i]) * (unsigned long long)(i % 1000003u + 1u);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if ((threadIdx.x & 31) == 0) atomicAdd(acc, s);
+}
+// fp[0] = fingerprint just accumulated, fp[1] = previous one, fp[2] = previous one is valid
+__global__ void k_fingerprint_decide(unsigned long long* fp, int* skip, int force) {
+    *skip = (!force && fp[2] == 1ull && fp[0] == fp[1]) ? 1 : 0;
+    fp[1] = fp[0];
+    fp[0] = 0ull;
+    fp[2] = 1ull;
+}
+
+__global__ void k_unit_norm(const float* __restrict__ x, float* __restrict__ y, int rows, int cols, float eps,
+                            const int* __restrict__ skip = nullptr) {
+    if (skip && *skip) return;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -107,7 +129,9 @@ __global__ void k_unit_norm(const float* __restrict__ x, float* __restrict__ y, 
 template <int M, typename Real>
 __global__ void __launch_bounds__(BlockFft<M, Real>::T)
 k_pair_spectra(const float* __restrict__ dict, int A, int atom_lo, int atom_hi,
-               const cpx<Real>* __restrict__ tw1, const cpx<Real>* __restrict__ tw2, C32* __restrict__ pairspec) {
+               const cpx<Real>* __restrict__ tw1, const cpx<Real>* __restrict__ tw2, C32* __restrict__ pairspec,
+               const int* __restrict__ skip = nullptr) {
+    if (skip && *skip) return;
     using F = BlockFft<M, Real>;
     using C = cpx<Real>;
     extern __shared__ __align__(16) unsigned char smraw[];
@@ -168,7 +192,9 @@ __device__ __forceinline__ void window_fft_body(const float* __restrict__ x, int
 template <int M>
 __global__ void __launch_bounds__(BlockFft<M, float>::T)
 k_window_fft(const float* __restrict__ src, long long row_stride, int row_len, const Win* __restrict__ win,
-             const C32* __restrict__ tw1, const C32* __restrict__ tw2, C32* __restrict__ winspec) {
+             const C32* __restrict__ tw1, const C32* __restrict__ tw2, C32* __restrict__ winspec,
+             const int* __restrict__ skip = nullptr) {
+    if (skip && *skip) return;
     using F = BlockFft<M, float>;
     extern __shared__ __align__(16) unsigned char smraw[];
     C32* sm = reinterpret_cast<C32*>(smraw);
@@ -215,6 +241,7 @@ struct CorrArgs {
     long long dense_row_stride;   // between windows' source rows
     long long dense_atom_stride;  // between atoms
     int dense_col_off;            // column = t0 + m + dense_col_off
+    const int* skip;              // optional device flag: nothing to do (unchanged dictionary, Gram build)
 };
 
 // Shared memory: [tw2: 256 complex][per transform: FFT buffer SMEM_CPX complex][per transform, only
@@ -231,6 +258,7 @@ struct CorrArgs {
 template <int M, int MODE>
 __global__ void __launch_bounds__((BlockFft<M, float>::T < 256 ? 256 : BlockFft<M, float>::T), MPB_CORR_MINB)
 k_corr(const CorrArgs a) {
+    if (a.skip && *a.skip) return;
     using F = BlockFft<M, float>;
     constexpr int TPB = F::T < 256 ? 256 : F::T;
     constexpr int NT = TPB / F::T;   // transforms (atom pairs) per CTA

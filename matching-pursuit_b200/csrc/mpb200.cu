@@ -126,21 +126,22 @@ static void free_plan(Plan* p) {
 // launches
 // ---------------------------------------------------------------------------
 static int launch_window_fft_ex(int M, const C32* tw1, const C32* tw2, const float* src, long long row_stride,
-                                int row_len, const Win* win, int nwin, C32* winspec, cudaStream_t st) {
+                                int row_len, const Win* win, int nwin, C32* winspec, cudaStream_t st,
+                                const int* skip = nullptr) {
     if (nwin <= 0) return MPB200_OK;
     MPB_DISPATCH_M(M, {
         using F = BlockFft<MM, float>;
         const size_t smem = (size_t)(F::SMEM_CPX + 256) * sizeof(C32);
         MPB_CUDA(allow_smem(k_window_fft<MM>, smem));
-        k_window_fft<MM><<<nwin, F::T, smem, st>>>(src, row_stride, row_len, win, tw1, tw2, winspec);
+        k_window_fft<MM><<<nwin, F::T, smem, st>>>(src, row_stride, row_len, win, tw1, tw2, winspec, skip);
     });
     MPB_LAUNCH_CHECK("k_window_fft");
     return MPB200_OK;
 }
 
 static int launch_window_fft(Plan* p, const float* src, long long row_stride, int row_len, const Win* win, int nwin,
-                             C32* winspec, cudaStream_t st) {
-    return launch_window_fft_ex(p->M, p->tw1, p->tw2, src, row_stride, row_len, win, nwin, winspec, st);
+                             C32* winspec, cudaStream_t st, const int* skip = nullptr) {
+    return launch_window_fft_ex(p->M, p->tw1, p->tw2, src, row_stride, row_len, win, nwin, winspec, st, skip);
 }
 
 template <int MODE>
@@ -411,9 +412,10 @@ static int step_refresh(Plan* p, int batch, cudaStream_t st) {
 static int build_gram(Plan* p, cudaStream_t st) {
     for (int k0 = 0; k0 < p->K; k0 += p->wcap) {
         const int n = p->K - k0 < p->wcap ? p->K - k0 : p->wcap;
-        int rc = launch_window_fft(p, p->dict, p->A, p->A, p->win_gram + k0, n, p->winspec, st);
+        int rc = launch_window_fft(p, p->dict, p->A, p->A, p->win_gram + k0, n, p->winspec, st, p->dict_skip);
         if (rc) return rc;
         CorrArgs a = base_corr_args(p);
+        a.skip = p->dict_skip;
         a.win = p->win_gram + k0;
         a.nwin = n;
         a.len = p->A;                      // valid outputs: t0 + m < len  <=>  m < 2A-1   (t0 = -(A-1))
@@ -433,7 +435,7 @@ static int build_pair_spectra(Plan* p, cudaStream_t st) {
         const size_t smem = (size_t)(F::SMEM_CPX + 256) * sizeof(cpx<double>);
         MPB_CUDA((allow_smem(k_pair_spectra<MM, double>, smem)));
         k_pair_spectra<MM, double><<<p->npairs, F::T, smem, st>>>(p->dict, p->A, p->lo, p->hi, p->tw1d, p->tw2d,
-                                                                   p->pairspec);
+                                                                   p->pairspec, p->dict_skip);
     });
     MPB_LAUNCH_CHECK("k_pair_spectra");
     return MPB200_OK;
@@ -446,10 +448,11 @@ static int build_sgram_tables(Plan* p, cudaStream_t st) {
         const size_t smem = (size_t)(F::SMEM_CPX + 256) * sizeof(cpx<double>);
         MPB_CUDA((allow_smem(k_pair_spectra<MM, double>, smem)));
         k_pair_spectra<MM, double><<<p->npairs, F::T, smem, st>>>(p->dict, p->A, p->lo, p->hi, p->tw1bd, p->tw2d,
-                                                                   p->pairspec2);
+                                                                   p->pairspec2, p->dict_skip);
     });
     MPB_LAUNCH_CHECK("k_pair_spectra");
-    return launch_window_fft_ex(p->M2, p->tw1b, p->tw2, p->dict, p->A, p->A, p->win_atoms, p->K, p->atomspec, st);
+    return launch_window_fft_ex(p->M2, p->tw1b, p->tw2, p->dict, p->A, p->A, p->win_atoms, p->K, p->atomspec, st,
+                                p->dict_skip);
 }
 
 // With CUDA's lazy module loading the FIRST use of a kernel may synchronise the context.  A pursuit whose
@@ -638,6 +641,8 @@ int mpb200_plan_create(mpb200_plan_t* out, int n_atoms, int atom_size, int n_sam
     MPB_TRY(dev_alloc(p, &p->row_pos, (size_t)alloc_batch * p->nloc));
     MPB_TRY(dev_alloc(p, &p->residual, (size_t)alloc_batch * n_samples));
     MPB_TRY(dev_alloc(p, &p->best, (size_t)alloc_batch));
+    MPB_TRY(dev_alloc(p, &p->fp, (size_t)3));
+    MPB_TRY(dev_alloc(p, &p->dict_skip, (size_t)1));
     std::vector<Win> wg;
     if (mode == MPB200_MODE_GRAM) {
         p->gram_bytes = gram_bytes;
@@ -695,6 +700,8 @@ int mpb200_plan_create(mpb200_plan_t* out, int n_atoms, int atom_size, int n_sam
         up(p->tw1b, t1b.data(), t1b.size() * sizeof(t1b[0]));
         up(p->tw1bd, t1bd.data(), t1bd.size() * sizeof(t1bd[0]));
     }
+    if (e == cudaSuccess) e = cudaMemset(p->fp, 0, 3 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(p->dict_skip, 0, sizeof(int));
     if (p->gram && e == cudaSuccess) e = cudaMemset(p->gram, 0, (size_t)n_atoms * p->nloc * p->GS * sizeof(float));
     if (e != cudaSuccess) {
         free_plan(p);
@@ -767,8 +774,17 @@ static int set_dictionary_impl(mpb200_plan_t plan, const float* d, bool normaliz
     if (rc) return rc;
     if (!d) return fail(MPB200_EINVAL, "null dictionary");
     cudaStream_t st = (cudaStream_t)stream;
+    // unchanged dictionary? decided on the device: the kernels below return at once when it is
+    const size_t n_dict = (size_t)p->K * p->A;
+    int fgrid = (int)((n_dict + 256 * 8 - 1) / (256 * 8));
+    if (fgrid > p->sm_count * 8) fgrid = p->sm_count * 8;
+    k_fingerprint<<<fgrid, 256, 0, st>>>(d, n_dict, p->fp);
+    MPB_LAUNCH_CHECK("k_fingerprint");
+    k_fingerprint_decide<<<1, 1, 0, st>>>(p->fp, p->dict_skip, (!p->dict_set || p->last_normalize != (int)normalize) ? 1 : 0);
+    MPB_LAUNCH_CHECK("k_fingerprint_decide");
+    p->last_normalize = (int)normalize;
     if (normalize) {
-        k_unit_norm<<<(p->K + 7) / 8, 256, 0, st>>>(d, p->dict, p->K, p->A, 1e-8f);
+        k_unit_norm<<<(p->K + 7) / 8, 256, 0, st>>>(d, p->dict, p->K, p->A, 1e-8f, p->dict_skip);
         MPB_LAUNCH_CHECK("k_unit_norm");
     } else {
         MPB_CUDA(cudaMemcpyAsync(p->dict, d, (size_t)p->K * p->A * sizeof(float), cudaMemcpyDeviceToDevice, st));

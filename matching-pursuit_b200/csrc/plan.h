@@ -64,6 +64,11 @@ struct Plan {
     unsigned xseq = 0;                      // exchanges issued so far (sequence number of the next one is xseq + 1)
     bool xconnected = false;
 
+    // unchanged-dictionary detection (device side, no host synchronisation)
+    unsigned long long* fp = nullptr;       // [0] fingerprint being accumulated, [1] previous, [2] previous valid
+    int* dict_skip = nullptr;               // device flag read by the table-building kernels
+    int last_normalize = -1;
+
     // staging for the host-buffer entry point
     float* d_signal = nullptr;
     int32_t *d_atom = nullptr, *d_pos = nullptr;

@@ -498,6 +498,26 @@ def test_non_finite_input_is_memory_safe(mode):
     assert np.array_equal(atom[1:], ref[0]) and np.array_equal(pos[1:], ref[1]) and np.array_equal(val[1:], ref[2])
 
 
+def test_dictionary_tables_follow_the_tensor_even_through_dot_data():
+    """The plan skips rebuilding its tables when handed the same, unmodified dictionary tensor again -- and must
+    not be fooled by in-place writes, including writes through `.data`, which do not bump torch's version counter."""
+    k, a, n, b, s = 16, 64, 2048, 2, 10
+    d = O.make_dictionary(k, a, seed=1).to(DEV)
+    sig = O.make_planted_signals(d.cpu(), b, n, 6, seed=2).to(DEV)
+    plan = mpb.Plan(k, a, n, b, device=DEV, mode="recorrelate")
+    first = [t.cpu() for t in plan.set_dictionary(d).sparse_code(sig, s)]
+    again = [t.cpu() for t in plan.set_dictionary(d).sparse_code(sig, s)]          # cached tables
+    assert all(torch.equal(x, y) for x, y in zip(first, again))
+    d2 = O.make_dictionary(k, a, seed=7).to(DEV)
+    want = [t.cpu() for t in mpb.Plan(k, a, n, b, device=DEV, mode="recorrelate").set_dictionary(d2).sparse_code(sig, s)]
+    d.data.copy_(d2)                                                                # same object, same _version
+    got = [t.cpu() for t in plan.set_dictionary(d).sparse_code(sig, s)]
+    assert all(torch.equal(x, y) for x, y in zip(want, got))
+    d.copy_(O.make_dictionary(k, a, seed=1).to(DEV))                               # versioned in-place write
+    back = [t.cpu() for t in plan.set_dictionary(d).sparse_code(sig, s)]
+    assert all(torch.equal(x, y) for x, y in zip(first, back))
+
+
 def test_errors():
     with pytest.raises(mpb.MpbError):
         mpb.Plan(4, 5000, 128, 1, device=DEV)            # window FFT longer than supported
