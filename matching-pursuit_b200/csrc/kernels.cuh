@@ -1079,16 +1079,18 @@ k_delta(const DeltaArgs a) {
             // (row, block) tasks are dealt round-robin to the warps; the refreshed (max, position) pairs
             // only go to shared memory here -- the row warps publish them to bm_val / bm_pos.
             const int ntask = second ? 2 * nvb : nvb;
-            if (blk == 256 && start + (nvb << 8) <= a.N) {       // the common shape: whole blocks, two float4 per lane
+            if (blk >= 128 && start + (nvb << a.blk_shift) <= a.N) {   // whole blocks of 128 / 256: one / two float4 per lane
                 const float* __restrict__ rowl = st0 + 4 * lane;
-                int o = warp << 8, slot = warp;                   // offset into the staging rows, slot in sBV
-                for (int task = warp; task < ntask; task += NW, o += NW << 8, slot += NW) {
+                const int sh = a.blk_shift;
+                int o = warp << sh, slot = warp;                  // offset into the staging rows, slot in sBV
+                for (int task = warp; task < ntask; task += NW, o += NW << sh, slot += NW) {
                     if (task >= nvb && task - NW < nvb) {         // crossing from row 0 to row 1
-                        o += a.cap - (nvb << 8);
+                        o += a.cap - (nvb << sh);
                         slot += 32 - nvb;
                     }
                     const float4 c0 = *reinterpret_cast<const float4*>(rowl + o);
-                    const float4 c1 = *reinterpret_cast<const float4*>(rowl + o + 128);
+                    float4 c1 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                    if (blk == 256) c1 = *reinterpret_cast<const float4*>(rowl + o + 128);
                     float v = fmaxf(fmaxf(fmaxf(c0.x, c0.y), fmaxf(c0.z, c0.w)),
                                     fmaxf(fmaxf(c1.x, c1.y), fmaxf(c1.z, c1.w)));
                     const int kmax = __reduce_max_sync(0xffffffffu, float_key(v));
@@ -1104,10 +1106,45 @@ k_delta(const DeltaArgs a) {
                     at = (c0.y + 0.0f == v) ? 1 : at;
                     at = (c0.x + 0.0f == v) ? 0 : at;
                     at = __reduce_min_sync(0xffffffffu, at == INT_MAX ? at : at + 4 * lane);
-                    // position = start + (block index within its row) * 256 + at
+                    // position = start + (block index within its row) * blk + at
                     if (lane == 0)
                         sBV[slot] = make_float2(v, __int_as_float(at == INT_MAX ? INT_MAX
-                                                                                 : start + ((slot & 31) << 8) + at));
+                                                                                 : start + ((slot & 31) << sh) + at));
+                }
+            } else if (blk <= 64 && start + (nvb << a.blk_shift) <= a.N) {
+                // short atoms (blocks of 16 / 32 / 64 positions, whole blocks inside the signal): a task is 64
+                // consecutive staged positions of one row = 4 / 2 / 1 blocks, two conflict-free loads per lane,
+                // reduced with redux.sync over the lanes that share a block.
+                const int span = nvb << a.blk_shift;                   // staged positions that belong to blocks
+                const int per_row = (span + 63) >> 6;                  // tasks per row
+                const int rows_here = second ? 2 : 1;
+                const unsigned seg = blk == 16 ? (lane < 16 ? 0x0000ffffu : 0xffff0000u) : 0xffffffffu;
+                for (int task = warp; task < rows_here * per_row; task += NW) {
+                    const int which = task >= per_row ? 1 : 0;
+                    const int j0 = ((task - which * per_row) << 6) + lane, j1 = j0 + 32;
+                    const float* __restrict__ row = st0 + which * a.cap;
+                    const float c0 = j0 < span ? row[j0] : -INFINITY;
+                    const float c1 = j1 < span ? row[j1] : -INFINITY;
+                    float v0 = c0, v1 = c1;
+                    if (blk == 64) v0 = v1 = fmaxf(c0, c1);            // one block spans both loads
+                    int k0 = __reduce_max_sync(seg, float_key(v0));
+                    int k1 = blk == 64 ? k0 : __reduce_max_sync(seg, float_key(v1));
+                    v0 = __int_as_float(k0 ^ ((k0 >> 31) & 0x7fffffff));
+                    v1 = __int_as_float(k1 ^ ((k1 >> 31) & 0x7fffffff));
+                    if (!(v0 == v0)) v0 = -INFINITY;                   // a NaN never wins
+                    if (!(v1 == v1)) v1 = -INFINITY;
+                    int a0 = (c0 + 0.0f == v0) ? j0 : INT_MAX;
+                    int a1 = (c1 + 0.0f == v1) ? j1 : INT_MAX;
+                    if (blk == 64) a0 = a1 = min(a0, a1);
+                    a0 = __reduce_min_sync(seg, a0);
+                    if (blk != 64) a1 = __reduce_min_sync(seg, a1);
+                    const bool leader = blk == 16 ? (lane & 15) == 0 : lane == 0;
+                    if (leader) {
+                        const int b0 = j0 >> a.blk_shift, b1 = j1 >> a.blk_shift;   // block indices relative to blk0
+                        if (b0 < nvb) sBV[which * 32 + b0] = make_float2(v0, __int_as_float(a0 == INT_MAX ? INT_MAX : start + a0));
+                        if (blk != 64 && b1 < nvb)
+                            sBV[which * 32 + b1] = make_float2(v1, __int_as_float(a1 == INT_MAX ? INT_MAX : start + a1));
+                    }
                 }
             } else {
                 int which = 0, i = warp;
