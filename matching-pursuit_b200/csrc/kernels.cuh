@@ -702,8 +702,11 @@ struct GramArgs {
 // row is read with scalar loads because its offset t - p + A - 1 has arbitrary alignment).
 // BLK >= 128: a block is BLK/128 chunks, reduced over the whole warp; BLK < 128: a chunk holds
 // 128/BLK blocks, reduced over segments of BLK/4 lanes.  Lane i ends up holding refreshed block i.
+#ifndef MPB_GRAM_MINB
+#define MPB_GRAM_MINB 5      // CTAs per SM the register allocation of k_gram_update aims at (4: 0.163, 5: 0.157, 8: 0.198 ms at configs[1])
+#endif
 template <int BLK>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, MPB_GRAM_MINB)
 k_gram_update(const GramArgs a) {
     static_assert(BLK >= 16 && BLK <= 256, "block size");
     constexpr int LPB = BLK >= 128 ? 32 : BLK / 4;         // lanes that share a block inside a chunk
