@@ -92,9 +92,11 @@ def _events_from_packed(atom: torch.Tensor, batch_idx: torch.Tensor, pos: torch.
     a_host = atom.tolist()
     b_host = batch_idx.tolist()
     a_size = rows.shape[1]
-    pos2 = pos.view(-1, 1, 1)
-    rows3 = rows.view(-1, 1, 1, a_size)
-    out = EventList((a_host[e], b_host[e], pos2[e], rows3[e]) for e in range(len(a_host)))
+    # one unbind per array instead of two Python-level indexing calls per event (the tuples are the reference's
+    # format, modules/matchingpursuit.py:305-321; building them dominated small-dictionary calls)
+    pos_views = pos.view(-1, 1, 1).unbind(0) if len(a_host) else ()
+    row_views = rows.view(-1, 1, 1, a_size).unbind(0) if len(a_host) else ()
+    out = EventList(zip(a_host, b_host, pos_views, row_views))
     out.packed = (atom, batch_idx, pos, rows)
     return out
 
