@@ -29,6 +29,9 @@ constexpr int MODE_DENSE = 4;
 #define MPB_TWGEN 1   // pass-1 twiddles generated from one table entry (k_delta: 4.81 -> 4.63 ms per 128-signal iteration;
                       // the same trick on the shared-memory pass-2 table measured slower and is not kept)
 #endif
+#ifndef MPB_CORR_LEAN
+#define MPB_CORR_LEAN 1    // redux.sync block maxima in k_corr for whole blocks of 256 positions
+#endif
 #ifndef MPB_TWGEN_CORR
 #define MPB_TWGEN_CORR 0   // the same in k_corr
 #endif
@@ -54,6 +57,19 @@ __device__ __forceinline__ void warp_argmax(float& v, int& i) {
         int oi = __shfl_xor_sync(0xffffffffu, i, off);
         take_better(v, i, ov, oi);
     }
+}
+
+// Order-preserving map float -> int (for redux.sync max); -0 is folded into +0 first.
+__device__ __forceinline__ int float_key(float v) {
+    int k = __float_as_int(v + 0.0f);
+    return k ^ ((k >> 31) & 0x7fffffff);
+}
+// Warp (max, lowest position of the max): two redux.sync instead of a shuffle tree.
+__device__ __forceinline__ void warp_argmax_redux(float& v, int& at) {
+    const int key = float_key(v);
+    const int kmax = __reduce_max_sync(0xffffffffu, key);
+    at = __reduce_min_sync(0xffffffffu, key == kmax ? at : INT_MAX);
+    v = __int_as_float(kmax ^ ((kmax >> 31) & 0x7fffffff));
 }
 
 // Rescan of one map row's block maxima outside the refreshed blocks [blk0, blk0 + nvb): folds this lane's
@@ -331,19 +347,42 @@ k_corr(const CorrArgs a) {
                 const int hi = min((i + 1) * blk, limit);
                 float va = -INFINITY, vb = -INFINITY;
                 int ia = INT_MAX, ib = INT_MAX;
-                for (int m = i * blk + lane; m < hi; m += 32) {
-                    const float2 c = sY[m];
-                    if (c.x > va) { va = c.x; ia = m; }
-                    if (c.y > vb) { vb = c.y; ib = m; }
-                }
+                if (MPB_CORR_LEAN && blk == 256 && hi == (i + 1) * 256) {
+                    // whole block of 256: eight (atom 2q, atom 2q+1) pairs per lane, value maxima by fmax +
+                    // redux.sync on an order-preserving key, first position by an equality scan + redux.sync.min
+                    float2 c[8];
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {      // the two reductions interleave
-                    const float oa = __shfl_xor_sync(0xffffffffu, va, off);
-                    const int pa = __shfl_xor_sync(0xffffffffu, ia, off);
-                    const float ob = __shfl_xor_sync(0xffffffffu, vb, off);
-                    const int pb = __shfl_xor_sync(0xffffffffu, ib, off);
-                    take_better(va, ia, oa, pa);
-                    take_better(vb, ib, ob, pb);
+                    for (int j = 0; j < 8; ++j) c[j] = sY[i * 256 + lane + 32 * j];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { va = fmaxf(va, c[j].x); vb = fmaxf(vb, c[j].y); }
+                    const int ka = __reduce_max_sync(0xffffffffu, float_key(va));
+                    const int kb = __reduce_max_sync(0xffffffffu, float_key(vb));
+                    va = __int_as_float(ka ^ ((ka >> 31) & 0x7fffffff));
+                    vb = __int_as_float(kb ^ ((kb >> 31) & 0x7fffffff));
+                    if (!(va == va)) va = -INFINITY;          // a NaN never wins
+                    if (!(vb == vb)) vb = -INFINITY;
+#pragma unroll
+                    for (int j = 7; j >= 0; --j) {            // descending: the lowest matching position survives
+                        ia = (c[j].x + 0.0f == va) ? i * 256 + lane + 32 * j : ia;
+                        ib = (c[j].y + 0.0f == vb) ? i * 256 + lane + 32 * j : ib;
+                    }
+                    ia = __reduce_min_sync(0xffffffffu, ia);
+                    ib = __reduce_min_sync(0xffffffffu, ib);
+                } else {
+                    for (int m = i * blk + lane; m < hi; m += 32) {
+                        const float2 c = sY[m];
+                        if (c.x > va) { va = c.x; ia = m; }
+                        if (c.y > vb) { vb = c.y; ib = m; }
+                    }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {      // the two reductions interleave
+                        const float oa = __shfl_xor_sync(0xffffffffu, va, off);
+                        const int pa = __shfl_xor_sync(0xffffffffu, ia, off);
+                        const float ob = __shfl_xor_sync(0xffffffffu, vb, off);
+                        const int pb = __shfl_xor_sync(0xffffffffu, ib, off);
+                        take_better(va, ia, oa, pa);
+                        take_better(vb, ib, ob, pb);
+                    }
                 }
                 if (lane == 0 && q_ok) {
                     const int pa = (ia == INT_MAX) ? INT_MAX : wi.t0 + ia;
@@ -863,19 +902,6 @@ __device__ __forceinline__ void bulk_store(void* gmem_dst, const void* smem_src,
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// Order-preserving map float -> int (for redux.sync max); -0 is folded into +0 first.
-__device__ __forceinline__ int float_key(float v) {
-    int k = __float_as_int(v + 0.0f);
-    return k ^ ((k >> 31) & 0x7fffffff);
-}
-// Warp (max, lowest position of the max): two redux.sync instead of a shuffle tree.
-__device__ __forceinline__ void warp_argmax_redux(float& v, int& at) {
-    const int key = float_key(v);
-    const int kmax = __reduce_max_sync(0xffffffffu, key);
-    at = __reduce_min_sync(0xffffffffu, key == kmax ? at : INT_MAX);
-    v = __int_as_float(kmax ^ ((kmax >> 31) & 0x7fffffff));
-}
 
 // ---------------------------------------------------------------------------
 // SPECTRAL-GRAM mode update ("the Gram row is synthesised, not stored").  For signal b with winner
