@@ -347,27 +347,35 @@ k_corr(const CorrArgs a) {
                 const int hi = min((i + 1) * blk, limit);
                 float va = -INFINITY, vb = -INFINITY;
                 int ia = INT_MAX, ib = INT_MAX;
-                if (MPB_CORR_LEAN && blk == 256 && hi == (i + 1) * 256) {
-                    // whole block of 256: eight (atom 2q, atom 2q+1) pairs per lane, value maxima by fmax +
-                    // redux.sync on an order-preserving key, first position by an equality scan + redux.sync.min
-                    float2 c[8];
+                if (MPB_CORR_LEAN && blk >= 32 && hi == (i + 1) * blk) {
+                    // whole block of 32..256 positions: NJ = blk/32 (atom 2q, atom 2q+1) pairs per lane, value maxima
+                    // by fmax + redux.sync on an order-preserving key, first position by an equality scan +
+                    // redux.sync.min
+                    auto lean = [&](auto njc) {
+                        constexpr int NJ = decltype(njc)::value;
+                        float2 c[NJ];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) c[j] = sY[i * 256 + lane + 32 * j];
+                        for (int j = 0; j < NJ; ++j) c[j] = sY[i * blk + lane + 32 * j];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) { va = fmaxf(va, c[j].x); vb = fmaxf(vb, c[j].y); }
-                    const int ka = __reduce_max_sync(0xffffffffu, float_key(va));
-                    const int kb = __reduce_max_sync(0xffffffffu, float_key(vb));
-                    va = __int_as_float(ka ^ ((ka >> 31) & 0x7fffffff));
-                    vb = __int_as_float(kb ^ ((kb >> 31) & 0x7fffffff));
-                    if (!(va == va)) va = -INFINITY;          // a NaN never wins
-                    if (!(vb == vb)) vb = -INFINITY;
+                        for (int j = 0; j < NJ; ++j) { va = fmaxf(va, c[j].x); vb = fmaxf(vb, c[j].y); }
+                        const int ka = __reduce_max_sync(0xffffffffu, float_key(va));
+                        const int kb = __reduce_max_sync(0xffffffffu, float_key(vb));
+                        va = __int_as_float(ka ^ ((ka >> 31) & 0x7fffffff));
+                        vb = __int_as_float(kb ^ ((kb >> 31) & 0x7fffffff));
+                        if (!(va == va)) va = -INFINITY;          // a NaN never wins
+                        if (!(vb == vb)) vb = -INFINITY;
 #pragma unroll
-                    for (int j = 7; j >= 0; --j) {            // descending: the lowest matching position survives
-                        ia = (c[j].x + 0.0f == va) ? i * 256 + lane + 32 * j : ia;
-                        ib = (c[j].y + 0.0f == vb) ? i * 256 + lane + 32 * j : ib;
-                    }
-                    ia = __reduce_min_sync(0xffffffffu, ia);
-                    ib = __reduce_min_sync(0xffffffffu, ib);
+                        for (int j = NJ - 1; j >= 0; --j) {       // descending: the lowest matching position survives
+                            ia = (c[j].x + 0.0f == va) ? i * blk + lane + 32 * j : ia;
+                            ib = (c[j].y + 0.0f == vb) ? i * blk + lane + 32 * j : ib;
+                        }
+                        ia = __reduce_min_sync(0xffffffffu, ia);
+                        ib = __reduce_min_sync(0xffffffffu, ib);
+                    };
+                    if (blk == 256) lean(std::integral_constant<int, 8>{});
+                    else if (blk == 128) lean(std::integral_constant<int, 4>{});
+                    else if (blk == 64) lean(std::integral_constant<int, 2>{});
+                    else lean(std::integral_constant<int, 1>{});
                 } else {
                     for (int m = i * blk + lane; m < hi; m += 32) {
                         const float2 c = sY[m];
