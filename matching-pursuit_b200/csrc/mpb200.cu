@@ -340,6 +340,7 @@ static int step_refresh(Plan* p, int batch, cudaStream_t st) {
                 }
                 d.ngroups = (p->npairs + NT - 1) / NT;
                 const long long items = (long long)d.ngroups * batch;
+                if (items >= (1LL << 31)) return fail(MPB200_EINVAL, "SGRAM: more than 2^31 (pair, signal) work items per launch");
                 long long ctas = (long long)p->sm_count * p->delta_occ;
                 if (ctas > items) ctas = items;
                 k_delta<MM><<<(unsigned)ctas, TPB, smem, st>>>(d);
@@ -526,11 +527,14 @@ int mpb200_plan_create(mpb200_plan_t* out, int n_atoms, int atom_size, int n_sam
     cudaError_t ce = cudaGetDeviceCount(&count);
     if (ce != cudaSuccess || count == 0)
         return fail(MPB200_ECUDA, "no CUDA device: this library has no CPU path");
-    Plan* p = new Plan();
-    MPB_CUDA(cudaGetDevice(&p->device));
-    cudaDeviceProp prop;
-    MPB_CUDA(cudaGetDeviceProperties(&prop, p->device));
-    p->sm_count = prop.multiProcessorCount;
+    int device = 0, sm_count = 0;
+    size_t free_b = 0, total_b = 0;
+    MPB_CUDA(cudaGetDevice(&device));
+    MPB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+    MPB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    Plan* p = new Plan();           // from here on every failure path goes through free_plan
+    p->device = device;
+    p->sm_count = sm_count;
     p->K = n_atoms;
     p->A = atom_size;
     p->N = n_samples;
@@ -558,8 +562,6 @@ int mpb200_plan_create(mpb200_plan_t* out, int n_atoms, int atom_size, int n_sam
     int M2 = 512;
     while (M2 < 2 * atom_size) M2 *= 2;
     const int nvb_max = (2 * atom_size - 2) / p->blk + 2;
-    size_t free_b = 0, total_b = 0;
-    MPB_CUDA(cudaMemGetInfo(&free_b, &total_b));
     // per-signal bytes of the structures every mode keeps + the resident map
     const uint64_t per_signal = map_row_bytes + (uint64_t)p->nloc * p->NB * 8 + (uint64_t)p->nloc * 8 +
                                 (uint64_t)n_samples * 4;
