@@ -137,6 +137,10 @@ class AtomShardedPursuit:
         eng = self.engine
         if self.exchange == "p2p" and self.world > 1:
             atom, pos, val, res = eng.plan.sparse_code(signal, n_steps, want_residual=True)
+            if eng.plan.exchange_timed_out():          # synchronises; a peer did not deliver a record within 20 s
+                from ._lib import MpbError
+                raise MpbError("atom-sharded pursuit: a candidate record from another rank did not arrive in time; "
+                               "the results of this call are not valid on this rank")
             return atom, pos, val, res
         eng.begin(signal)
         b = signal.shape[0]
