@@ -271,8 +271,12 @@ struct CorrArgs {
 #ifndef MPB_CORR_SEP
 #define MPB_CORR_SEP 0       // 1: step kernels stage their outputs in a separate shared buffer (costs the 3rd CTA)
 #endif
+#ifndef MPB_CORR_MINB_DENSE
+#define MPB_CORR_MINB_DENSE 2   // instantiations that also write the dense map keep their outputs live longer: 128 registers (first pass of the map modes 67 -> 52 ms per 128 signals)
+#endif
 template <int M, int MODE>
-__global__ void __launch_bounds__((BlockFft<M, float>::T < 256 ? 256 : BlockFft<M, float>::T), MPB_CORR_MINB)
+__global__ void __launch_bounds__((BlockFft<M, float>::T < 256 ? 256 : BlockFft<M, float>::T),
+                                  ((MODE & MODE_DENSE) ? MPB_CORR_MINB_DENSE : MPB_CORR_MINB))
 k_corr(const CorrArgs a) {
     if (a.skip && *a.skip) return;
     using F = BlockFft<M, float>;
