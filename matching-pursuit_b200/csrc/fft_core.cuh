@@ -33,6 +33,19 @@ struct cpx {
 
 template <typename T> MPB_HD cpx<T> operator+(cpx<T> a, cpx<T> b) { return {a.x + b.x, a.y + b.y}; }
 template <typename T> MPB_HD cpx<T> operator-(cpx<T> a, cpx<T> b) { return {a.x - b.x, a.y - b.y}; }
+#ifndef MPB_F32X2
+#define MPB_F32X2 1   // complex add/sub as Blackwell packed fp32x2 instructions (FADD2 / FFMA2: one issue slot for both parts; k_delta -1.8%, k_corr -4.8%)
+#endif
+#if MPB_F32X2 && defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+__device__ __forceinline__ cpx<float> operator+(cpx<float> a, cpx<float> b) {
+    const float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+    return {r.x, r.y};
+}
+__device__ __forceinline__ cpx<float> operator-(cpx<float> a, cpx<float> b) {
+    const float2 r = __ffma2_rn(make_float2(b.x, b.y), make_float2(-1.f, -1.f), make_float2(a.x, a.y));
+    return {r.x, r.y};
+}
+#endif
 template <typename T> MPB_HD cpx<T> cmul(cpx<T> a, cpx<T> b) {
     return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
 }
