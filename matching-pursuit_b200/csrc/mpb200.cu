@@ -1,6 +1,6 @@
 // mpb200.cu -- plan management and the extern "C" entry points of include/mpb200.h.
 //
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17
 //             -Xcompiler -fPIC -shared -o libmpb200.so mpb200.cu fftconv.cu
 #include <atomic>
 #include <cmath>
