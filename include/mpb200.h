@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MPB200_VERSION 100
+#define MPB200_VERSION 110   /* 1.1: SGRAM mode, fused atom-sharded exchange, band limit */
 
 #define MPB200_OK 0
 #define MPB200_EINVAL (-1)   /* bad argument / unsupported shape */
