@@ -67,7 +67,13 @@ def parse_args():
                     help="c5 only: winner exchange fused into the pursuit over peer memory, or per-step NCCL all-gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--max-seconds", type=float, default=700.0,
+                    help="wall-clock budget of the whole command: the W warm-up and K timed steps are always run as "
+                         "asked; the legs after them (end-to-end steps, CPU sample, atom-sharded sub-record, strong-"
+                         "scaling leg) shrink to what is left")
+    ap.add_argument("--e2e-steps", type=int, default=2, help="steps of the end-to-end leg (at most --steps)")
+    ap.add_argument("--no-atom-sharded", action="store_true", help="skip the configs[4] sub-record")
     return ap.parse_args()
 
 
@@ -214,10 +220,15 @@ def run_reference(args):
     sample = (f"each step = {iters} greedy iterations on 1 signal x {n} samples with the {k}x{a} dictionary "
               f"({'FFT' if kw else 'conv1d'} correlation form, {cores} threads)")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC_BY_WORKLOAD.get(args.workload, METRIC), "value": value, "unit": UNIT,
+        "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic (planted atoms + noise, seeded; dictionary U(-1,1) unit-normed)",
+        # same keys as the repo arm's config; the CPU cannot run the whole workload (weeks), so every step is the
+        # bounded sample named in cpu_baseline.sample -- of the same dictionary, signal length and metric
+        "config": {"workload": desc, "batch_per_gpu": batch, "n_samples": n, "n_atoms": k, "atom_size": a,
+                   "iterations": s, "sampled": {"signals": 1, "iterations_per_step": iters}},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "cpu_model": cpu_model(), "torch_threads": torch.get_num_threads()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -328,40 +339,31 @@ def run_multiband(args):
 # --------------------------------------------------------------------------
 # atom-sharded workload (configs[4])
 # --------------------------------------------------------------------------
-def run_atom_sharded(args):
-    import torch
-    import torch.distributed as dist
-    import matching_pursuit_b200 as mpb
+def measure_atom_sharded(torch, dist, mpb, dev, world, rank, iterations, exchange, mode, steps=1, warmup=1,
+                         latency_iterations=512):
+    """configs[4] on the `world` GPUs of this job: residual and dictionary replicated, rank g owns K/world atoms, one
+    winner exchange per iteration.  Timed: the whole pursuit (first pass + `iterations` iterations) with the exchange
+    fused into the pursuit kernels over peer memory (`exchange="p2p"`, the default) or as a host-driven per-step NCCL
+    all-gather (`"nccl"`).  The per-step collective latency is ALWAYS measured on the NCCL form (CUDA events around
+    every all_gather_into_tensor of one 16-byte record per rank).  Returns the record (same on every rank)."""
     from matching_pursuit_b200.distributed import AtomShardedPursuit
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    batch, n, k, a, s, desc = WORKLOADS["c5"]
-    if args.iterations:
-        s = args.iterations
+    batch, n, k, a, _, desc = WORKLOADS["c5"]
+    s = iterations
     d, sig = make_inputs(torch, mpb, dev, batch, n, k, a, n_events=min(s, 1024), seed=1)   # same on every rank
-    pursuit = AtomShardedPursuit(k, a, n, batch, device=dev, mode=args.mode, exchange=args.exchange).set_dictionary(d)
-    nccl_ref = pursuit if (args.exchange == "nccl" or world == 1) else \
-        AtomShardedPursuit(k, a, n, batch, device=dev, mode="recorrelate", exchange="nccl").set_dictionary(d)
+    pursuit = AtomShardedPursuit(k, a, n, batch, device=dev, mode=mode, exchange=exchange).set_dictionary(d)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         pursuit.run(sig, min(s, 64))
     barrier()
     launches0 = mpb.lib().mpb200_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         atom, pos, val, res = pursuit.run(sig, s)
     e1.record()
     barrier()
@@ -370,10 +372,18 @@ def run_atom_sharded(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
+    timed_out = pursuit.engine.plan.exchange_timed_out() if (exchange == "p2p" and world > 1) else False
+    plan_mode = pursuit.engine.plan.mode
     # separate, un-timed pass with events around every exchange: per-step collective latency of the NCCL form
-    nccl_ref.run(sig, min(s, 512), time_exchange=True)
+    if exchange == "nccl" or world == 1:
+        nccl_ref = pursuit
+    else:
+        nccl_ref = AtomShardedPursuit(k, a, n, batch, device=dev, mode="recorrelate", exchange="nccl").set_dictionary(d)
+    nccl_ref.run(sig, min(s, latency_iterations), time_exchange=True)
     ex = sorted(nccl_ref.exchange_ms)
-    timed_out = pursuit.engine.plan.exchange_timed_out() if (args.exchange == "p2p" and world > 1) else False
+    if nccl_ref is not pursuit:
+        nccl_ref.close()
+    pursuit.close()
     # all ranks must agree on the sequence
     if world > 1:
         chk = torch.stack([atom.double().sum(), pos.double().sum(), val.double().sum()])
@@ -383,25 +393,51 @@ def run_atom_sharded(args):
         agree = bool(torch.equal(lo, hi))
     else:
         agree = True
+    fused = exchange == "p2p" and world > 1
+    return {
+        "workload": desc, "n_gpus": world, "iterations": s, "steps": steps,
+        "atoms_per_s": s * steps / (ms_total / 1e3), "ms_per_step": ms_total / steps,
+        "us_per_iteration": 1e3 * ms_total / steps / s,
+        "atoms_per_rank": (k + world - 1) // world, "mode": plan_mode,
+        "exchange": ("fused into k_apply: 8-byte-atomic stores into peer mailboxes over NVLink" if fused else
+                     "per-step NCCL all_gather_into_tensor between local_best and apply"),
+        "exchange_timed_out": timed_out, "ranks_agree": agree, "gpu_launches": int(launches),
+        "exchange_latency_us": {"mean": 1e3 * sum(ex) / max(len(ex), 1), "p50": 1e3 * ex[len(ex) // 2] if ex else None,
+                                "p99": 1e3 * ex[min(len(ex) - 1, int(0.99 * len(ex)))] if ex else None,
+                                "samples": len(ex),
+                                "what": "CUDA-event time around the per-step NCCL all_gather_into_tensor of one "
+                                        "16-byte record per rank (NCCL form of the exchange; at 1 GPU there is no "
+                                        "collective and this is the empty event pair)"},
+    }
+
+
+def run_atom_sharded(args):
+    import torch
+    import torch.distributed as dist
+    import matching_pursuit_b200 as mpb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    s = args.iterations or WORKLOADS["c5"][4]
+    r = measure_atom_sharded(torch, dist, mpb, dev, world, rank, s, args.exchange, args.mode, steps=args.steps,
+                             warmup=args.warmup)
     if rank == 0:
         print(json.dumps({
-            "metric": "MP atoms/sec (16384x2048 dict, 2^20 sig, atom-sharded)", "value": s * args.steps / (ms_total / 1e3),
+            "metric": "MP atoms/sec (16384x2048 dict, 2^20 sig, atom-sharded)", "value": r["atoms_per_s"],
             "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic (planted atoms + noise, seeded)",
-            "config": {"workload": desc, "iterations": s, "atoms_per_rank": (k + world - 1) // world, "mode": pursuit.engine.plan.mode,
-                       "parallelism": f"atom-sharded x{world}",
-                       "exchange": ("fused into k_apply: 8-byte-atomic stores into peer mailboxes over NVLink"
-                                    if (args.exchange == "p2p" and world > 1) else
-                                    "per-step NCCL all_gather_into_tensor between local_best and apply")},
-            "exchange_timed_out": timed_out,
-            "gpu_launches": int(launches), "ranks_agree": agree,
-            "exchange_latency_ms": {"mean": sum(ex) / max(len(ex), 1), "p50": ex[len(ex) // 2] if ex else None,
-                                    "p99": ex[min(len(ex) - 1, int(0.99 * len(ex)))] if ex else None,
-                                    "what": "CUDA-event time around the per-step NCCL all_gather_into_tensor of "
-                                            "one 16-byte record per rank, measured on the NCCL form of the "
-                                            "exchange (0 at 1 GPU: no collective)"},
-            "us_per_iteration": 1e3 * ms_total / args.steps / s,
+            "config": {"workload": r["workload"], "iterations": s, "atoms_per_rank": r["atoms_per_rank"],
+                       "mode": r["mode"], "parallelism": f"atom-sharded x{world}", "exchange": r["exchange"]},
+            "exchange_timed_out": r["exchange_timed_out"], "gpu_launches": r["gpu_launches"],
+            "ranks_agree": r["ranks_agree"], "exchange_latency_us": r["exchange_latency_us"],
+            "us_per_iteration": r["us_per_iteration"],
         }), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -460,6 +496,11 @@ def main():
     hbm_peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json)") if peaks.get("hbm_gbs") else \
         (6650.0, "fallback (B200_PROFILING.md)")
 
+    t_start = time.perf_counter()
+
+    def left():          # seconds of the wall-clock budget that remain
+        return args.max_seconds - (time.perf_counter() - t_start)
+
     t_setup = time.perf_counter()
     d, sig = make_inputs(torch, mpb, dev, batch, n, k, a, n_events=min(s, 256), seed=1 + rank)
     plan = mpb.Plan(k, a, n, batch, mode=args.mode, device=dev)
@@ -476,9 +517,11 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput -------------------------------------
+    t_w = time.perf_counter()
     for _ in range(args.warmup):
         plan.sparse_code(sig, s, want_residual=True)
     barrier()
+    step_s = (time.perf_counter() - t_w) / max(args.warmup, 1)      # host estimate of one step, for the budget only
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -502,6 +545,16 @@ def main():
     value = atoms_per_step * args.steps / (ms_total / 1e3)
 
     # ---- end to end through the host-buffer C-ABI entry ------------------
+    # Same workload, same step; host signals in, events + residual out, copies inside the timed region.  The kernels
+    # are warm and the staging buffers were sized by the first call, so the leg is `e2e_steps` timed steps (at most
+    # --e2e-steps, at most K, and as many as the wall-clock budget still holds: a step is a whole pursuit of the
+    # batch, tens of seconds at the headline shape).  All ranks agree on the count.
+    def agree_min(x):
+        t_ = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_, op=dist.ReduceOp.MIN)
+        return float(t_.item())
+
     e2e = None
     if not args.no_e2e:
         sig_host = sig.cpu().pin_memory()
@@ -509,11 +562,15 @@ def main():
                 torch.empty(batch, s, dtype=torch.int32).pin_memory(),
                 torch.empty(batch, s, dtype=torch.float32).pin_memory(),
                 torch.empty(batch, n, dtype=torch.float32).pin_memory())
-        plan.sparse_code_host(sig_host, s, out=outs)          # warm-up (allocates staging)
+        reserve = 45.0                                          # CPU sample, sub-records, teardown
+        fit = int(agree_min((left() - reserve) / max(step_s, 1e-3)))
+        e2e_steps = max(1, min(args.e2e_steps, args.steps, fit))
+        if step_s < 1.0:                                        # cheap steps: also warm the host path once
+            plan.sparse_code_host(sig_host, s, out=outs)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(args.steps):
+        for _ in range(e2e_steps):
             plan.sparse_code_host(sig_host, s, out=outs)
         e1.record()
         barrier()
@@ -522,10 +579,51 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         h2d = sig_host.numel() * 4
         d2h = sum(o.numel() * 4 for o in outs)
-        e2e = {"value": atoms_per_step * args.steps / (float(te.item()) / 1e3), "unit": UNIT,
-               "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-               "api": "mpb200_sparse_code_host (Plan.sparse_code_host), pinned host buffers"}
+        e2e = {"value": atoms_per_step * e2e_steps / (float(te.item()) / 1e3), "unit": UNIT,
+               "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "steps": e2e_steps,
+               "ms_per_step": float(te.item()) / e2e_steps,
+               "api": "mpb200_sparse_code_host (Plan.sparse_code_host), pinned host buffers; "
+                      f"{e2e_steps} timed step(s) after the {args.warmup}+{args.steps} device-resident ones"}
+        del sig_host, outs
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- strong-scaling form of the same configuration --------------------
+    # BASELINE configs[2] as written: ONE batch of 1024 signals split over the N GPUs (the headline `value` above is
+    # the weak form: 1024 signals per GPU).  At N = 1 the two coincide.
+    strong = None
+    if args.workload == "c3" and standard:
+        if world == 1:
+            strong = {"global_batch": batch, "batch_per_gpu": batch, "value": value, "unit": UNIT,
+                      "ms_per_step": ms_total / args.steps, "steps": args.steps, "note": "identical to the weak form at 1 GPU"}
+        elif agree_min(left()) > 60.0 + step_s / world:
+            lo, hi = mpb.distributed.shard_batch(batch, world, rank)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            plan.sparse_code(sig[lo:hi], s, want_residual=True)
+            e1.record()
+            barrier()
+            ts = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+            strong = {"global_batch": batch, "batch_per_gpu": hi - lo, "value": batch * s / (float(ts.item()) / 1e3),
+                      "unit": UNIT, "ms_per_step": float(ts.item()), "steps": 1,
+                      "note": "one batch of 1024 signals split over the ranks, no collective; max over ranks"}
+
+    # ---- roofline inputs are read before the plan is released -------------
+    info = plan.info
+    plan_mode, plan_fft2, plan_resident, plan_bytes = plan.mode, plan.fft_size2, plan.resident_batch, int(plan.device_bytes)
+    plan.close()
+    del plan, sig, out
+    torch.cuda.empty_cache()
+
+    # ---- configs[4] sub-record: atom sharding with a per-step winner exchange ---------
+    atom_sharded = None
+    if args.workload == "c3" and standard and not args.no_atom_sharded and agree_min(left()) > 40.0:
+        try:
+            atom_sharded = measure_atom_sharded(torch, dist, mpb, dev, world, rank, 512, "p2p", "auto", steps=1, warmup=1,
+                                                latency_iterations=256)
+        except Exception as exc:                                 # the sub-record must never cost the headline line
+            atom_sharded = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     if rank != 0:
         if world > 1:
@@ -533,7 +631,6 @@ def main():
         return
 
     # ---- roofline of the dominant kernel ---------------------------------
-    info = plan.info
     m_fft, blk, nb = info.fft_size, info.block, info.n_blocks
     corr_ms, corr_n = kernel_times["recorrelate"]
     apply_ms, apply_n = kernel_times["apply"]
@@ -548,7 +645,7 @@ def main():
         + 8 * batch * k
     roofline = None
     gram_ms, gram_n = kernel_times["gram_update"]
-    if plan.mode == "gram" and gram_n:
+    if plan_mode == "gram" and gram_n:
         # dominant kernel in GRAM mode: k_gram_update.  Algorithmic bytes per launch:
         # per signal 4*K*W (Gram row read) + 8*K*W (map window read-modify-write), W = 2A-1.
         w = 2 * a - 1
@@ -559,21 +656,24 @@ def main():
                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                     "peak_source": peak_src, "traffic": None, "alg_bytes_per_launch": gram_bytes,
                     "ms_per_launch": gram_ms / gram_n, "share_of_step": gram_ms / ms_total}
-    elif plan.mode == "sgram" and gram_n:
+    elif plan_mode == "sgram" and gram_n:
         # dominant kernel in SGRAM mode: k_delta.  The Gram rows are synthesised from L2-resident spectra, so the
         # algorithmic HBM bytes per atom-step are the map window read-modify-write alone: 8*K*W, W = 2A-1
         # (SURVEY.md 8d "Gram incremental update" minus its 4*K*W table read).
         w = 2 * a - 1
-        n_sub = -(-batch // plan.resident_batch)
+        n_sub = -(-batch // plan_resident)
         per_launch_signals = batch / n_sub
         delta_bytes = 8 * k * w * per_launch_signals
         per_launch_s = gram_ms / gram_n / 1e3
         achieved = delta_bytes / per_launch_s / 1e9
-        flops = per_launch_signals * ((k + 1) // 2) * 5.0 * plan.fft_size2 * (plan.fft_size2.bit_length() - 1)
+        flops = per_launch_signals * ((k + 1) // 2) * 5.0 * plan_fft2 * (plan_fft2.bit_length() - 1)
         roofline = {"bound": "hbm", "kernel": "k_delta (Gram rows synthesised by inverse FFT of cached spectra; TMA-staged "
                                               "map window -= v * row; fused block/row maxima)",
                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                     "peak_source": peak_src, "traffic": measured_traffic("k_delta", args.workload, per_launch_signals),
+                    "traffic_source": "NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                      "k_delta launch from the committed `ncu --set full` capture "
+                                      "(profiles/traffic.json, bytes per signal) x signals per launch",
                     "alg_bytes_per_launch": delta_bytes, "signals_per_launch": per_launch_signals,
                     "ms_per_launch": gram_ms / gram_n, "share_of_step": gram_ms / ms_total,
                     "fp32": {"note": "secondary bound: nominal 5*M2*log2(M2) FLOP per inverse transform against the "
@@ -600,26 +700,31 @@ def main():
         "dtype": "f32", "data": "synthetic (planted atoms + noise, seeded; dictionary U(-1,1) unit-normed)",
         "config": {"workload": desc if standard else f"NON-STANDARD batch={batch} iterations={s} of: {desc}",
                    "batch_per_gpu": batch, "n_samples": n, "n_atoms": k, "atom_size": a, "iterations": s,
-                   "mode": plan.mode, "fft_size": m_fft, "fft_size2": plan.fft_size2, "block": blk,
-                   "resident_batch": plan.resident_batch,
+                   "mode": plan_mode, "fft_size": m_fft, "fft_size2": plan_fft2, "block": blk,
+                   "resident_batch": plan_resident,
                    "parallelism": f"batch-sharded x{world}, no collective",
-                   "l2": f"inputs larger than L2: plan working set {int(plan.device_bytes) >> 20} MiB + signals "
+                   "l2": f"inputs larger than L2: plan working set {plan_bytes >> 20} MiB + signals "
                          f"{batch * n * 4 >> 20} MiB"},
         "gpu_launches": int(launches), "clocks": clocks,
         "kernel_ms": {"first_pass": first_ms / max(first_n, 1), "apply_per_iteration": apply_ms / max(apply_n, 1),
                       "recorrelate_per_iteration": corr_ms / max(corr_n, 1),
                       "gram_update_per_iteration": gram_ms / max(gram_n, 1)},
         "setup": {"dictionary_tables_ms": dict_ms, "inputs_and_plan_s": setup_s,
-                  "plan_device_bytes": int(plan.device_bytes)},
+                  "plan_device_bytes": plan_bytes},
     }
     if e2e is not None:
         line["e2e"] = e2e
+    if strong is not None:
+        line["strong_scaling"] = strong
+    if atom_sharded is not None:
+        line["atom_sharded"] = atom_sharded
     if roofline is not None:
         line["roofline"] = roofline
     if not args.no_cpu_baseline and world == 1:
-        v, cores, sample, detail = cpu_atoms_per_second(torch, n, k, a, args.cpu_seconds)
+        v, cores, sample, detail = cpu_atoms_per_second(torch, n, k, a, max(4.0, min(args.cpu_seconds, left() - 10.0)))
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                                 "cpu_model": cpu_model(), "torch_threads": torch.get_num_threads()}
+    line["wall_s"] = round(time.perf_counter() - t_start, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MPB200_VERSION 110   /* 1.1: SGRAM mode, fused atom-sharded exchange, band limit */
+#define MPB200_VERSION 120   /* 1.2: exchange_disconnect, options FORCE_TABLES / MAX_STEPS, staged SGRAM spectra */
 
 #define MPB200_OK 0
 #define MPB200_EINVAL (-1)   /* bad argument / unsupported shape */
@@ -89,6 +89,14 @@ int mpb200_plan_info_get(mpb200_plan_t plan, mpb200_plan_info* info);
  * the residual every `value` iterations to bound the drift of the incremental
  * fp32 updates (0 = never, the default). */
 #define MPB200_OPT_REFRESH_EVERY 1
+/* MPB200_OPT_FORCE_TABLES (value != 0): the next mpb200_plan_set_dictionary* rebuilds every derived table even if
+ * the dictionary's fingerprint equals the previous one (see below). */
+#define MPB200_OPT_FORCE_TABLES 2
+/* MPB200_OPT_MAX_STEPS: size the device staging of mpb200_sparse_code_host for `value` iterations per signal now
+ * (plans are created with room for MPB200_DEFAULT_MAX_STEPS; a host call that needs more re-sizes on the spot,
+ * the only allocation the library makes after plan creation). */
+#define MPB200_OPT_MAX_STEPS 3
+#define MPB200_DEFAULT_MAX_STEPS 1024
 int mpb200_plan_set_option(mpb200_plan_t plan, int option, long long value);
 
 /* Per-kernel device timing of the pursuit loop (bench / profiling aid, no
@@ -107,7 +115,8 @@ int mpb200_plan_timing_read(mpb200_plan_t plan, double* ms_by_tag, int64_t* coun
  * reference at every entry (modules/matchingpursuit.py:254) -- and derives the
  * atom-pair spectra (and the Gram table in GRAM mode).  The caller's buffer is
  * not modified and may be freed once `stream` has passed this call.  A
- * fingerprint of `d` is compared ON THE DEVICE with the previous call's: when
+ * 128-bit fingerprint of `d` (two independently keyed sums of a full-avalanche mix of every (index, value))
+ * is compared ON THE DEVICE with the previous call's: when
  * the bits are unchanged the table-building kernels return at once, so callers
  * that keep the reference's habit of passing the dictionary with every call
  * do not pay for it, and nothing synchronises with the host. */
@@ -179,6 +188,10 @@ int mpb200_exchange_connect(mpb200_plan_t plan, const unsigned char* handles);
 int mpb200_exchange_mailbox(mpb200_plan_t plan, void** mailbox);
 int mpb200_exchange_connect_local(mpb200_plan_t plan, void* const* mailboxes);
 int mpb200_exchange_status(mpb200_plan_t plan, int* timed_out);
+/* Collective teardown, first half: waits for the plan's device work and unmaps the peers' mailboxes.  All ranks call
+ * it, synchronise among themselves (any transport), and only then destroy their plans -- freeing a mailbox that a
+ * peer still has mapped through CUDA IPC is undefined.  The plan is a plain un-connected sharded plan afterwards. */
+int mpb200_exchange_disconnect(mpb200_plan_t plan);
 
 /* Selection on a DENSE map fm (batch, n_atoms, n_samples) that the caller
  * already holds (a `compute_feature_map` callback result, or

@@ -18,6 +18,7 @@ LIB_PATH = os.environ.get("MPB200_LIBRARY") or os.path.join(HERE, "libmpb200.so"
 SOURCES = ["mpb200.cu", "fftconv.cu"]
 HEADERS = ["kernels.cuh", "fft_core.cuh", "bigfft.cuh", "types.h", "plan.h"]
 
+ABI_VERSION = 120    # MPB200_VERSION of include/mpb200.h this binding was written against
 MODE_AUTO, MODE_RECORRELATE, MODE_GRAM, MODE_FULL, MODE_SGRAM = 0, 1, 2, 3, 4
 MODES = {"auto": MODE_AUTO, "recorrelate": MODE_RECORRELATE, "gram": MODE_GRAM, "full": MODE_FULL,
          "sgram": MODE_SGRAM}
@@ -37,7 +38,9 @@ class MpbError(RuntimeError):
 def nvcc_command(out_path: str = LIB_PATH, extra=()):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = tuple(extra) + tuple(os.environ.get("MPB_NVCC_FLAGS", "").split())
-    return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    # --cudart shared: the process (torch) already carries a CUDA runtime; linking a second, static copy into the
+    # library would also drag every runtime entry point's name into the shipped artefact
+    return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--cudart", "shared",
             "-Xcompiler", "-fPIC", "-shared", *extra, "-o", out_path] + [os.path.join(CSRC, s) for s in SOURCES]
 
 
@@ -97,6 +100,7 @@ _SIGNATURES = {
     "mpb200_exchange_mailbox": (_i, [_p, _p]),
     "mpb200_exchange_connect_local": (_i, [_p, _p]),
     "mpb200_exchange_status": (_i, [_p, _p]),
+    "mpb200_exchange_disconnect": (_i, [_p]),
     "mpb200_band_limit": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "mpb200_spectral_band": (_i, [_p, _i, _i, _p, _i, _i, _i, _p]),
 }
@@ -112,6 +116,14 @@ def lib():
                 f"{LIB_PATH} is missing: the CUDA library has not been built and this package has no "
                 "CPU path.  Run: python -c \"import __graft_entry__ as g; g.build()\"")
         handle = C.CDLL(LIB_PATH)
+        handle.mpb200_version.restype = C.c_int
+        have = handle.mpb200_version() if hasattr(handle, "mpb200_version") else 0
+        missing = [name for name in _SIGNATURES if not hasattr(handle, name)]
+        if have < ABI_VERSION or missing:
+            raise MpbError(
+                f"{LIB_PATH} implements C ABI {have}, this package needs {ABI_VERSION}"
+                + (f" (missing: {', '.join(missing)})" if missing else "")
+                + "; rebuild it: python -c \"import __graft_entry__ as g; g.build()\"")
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args

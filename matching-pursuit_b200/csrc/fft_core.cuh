@@ -221,6 +221,19 @@ struct BlockFft {
         return (tl + T * u) + (M / 16) * m3;
     }
 
+    // Where pass 1 stores register slot e of thread tl.  Every thread owns its NB1 runs of R1 consecutive
+    // entries, so a spectrum that is STAGED in this layout (input bin in_index(tl, e) kept at slot_addr(tl, e))
+    // can be read and then overwritten by pass 1 without a barrier in between.
+    static MPB_HD int slot_addr(int tl, int e) {
+        const int u = e / R1, j1 = e % R1, c = tl + T * u;
+        return addr(j1, c >> 4, c & 15);
+    }
+    // The staged address of input bin j = j1*256 + c.
+    static MPB_HD int bin_addr(int j) {
+        const int j1 = j >> 8, c = j & 255;
+        return addr(j1, c >> 4, c & 15);
+    }
+
     // r[u*R1 + j1] holds in[j1*256 + c], c = tl + T*u.
     template <int DIR>
     static MPB_HD void pass1(C* r, int tl, C* sm, const C* __restrict__ tw1) {

@@ -77,8 +77,10 @@ __device__ __forceinline__ void warp_argmax_redux(float& v, int& at) {
 // samples) and the winner's own row is rescanned in every iteration, so the loads are issued 16 deep per
 // lane and only the values are scanned; the position of the lane's best block is fetched once at the end.
 // Equal values resolve to the lowest block, i.e. the lowest position.
+// bm_pos == nullptr: position-free tables (SGRAM): the candidate's "position" is the start of its block (any
+// position inside the lowest block that holds the maximum orders the same; k_apply resolves the exact one).
 __device__ __forceinline__ void rescan_row(const float* __restrict__ bm_val, const int* __restrict__ bm_pos, int NB,
-                                           int blk0, int nvb, int lane, float& v, int& at) {
+                                           int blk0, int nvb, int lane, float& v, int& at, int blk_shift = 0) {
     float bv = -INFINITY;
     int bi = -1;
     for (int i0 = lane; i0 < NB; i0 += 32 * 16) {
@@ -95,30 +97,50 @@ __device__ __forceinline__ void rescan_row(const float* __restrict__ bm_val, con
                 bi = i0 + 32 * u;
             }
     }
-    if (bi >= 0) take_better(v, at, bv, bm_pos[bi]);
+    if (bi >= 0) take_better(v, at, bv, bm_pos ? bm_pos[bi] : (bi << blk_shift));
 }
 
 // ---------------------------------------------------------------------------
 // y = x / (||x|| + eps) per row (modules/normalization.py:4-6). One warp per row.
 // ---------------------------------------------------------------------------
-// Dictionary fingerprint: position-weighted 64-bit sum of the float bits.  set_dictionary compares it on the
-// device with the previous one and the table-building kernels below return at once when nothing changed
-// (`skip`): the reference re-derives everything from `d` on every call (modules/matchingpursuit.py:254), and
-// callers that pass an unchanged dictionary again should not pay for it -- without a host synchronisation.
-__global__ void k_fingerprint(const float* __restrict__ d, size_t n, unsigned long long* __restrict__ acc) {
-    unsigned long long s = 0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        s += (unsigned long long)(unsigned)__float_as_int(d[i]) * (unsigned long long)(i % 1000003u + 1u);
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    if ((threadIdx.x & 31) == 0) atomicAdd(acc, s);
+// Dictionary fingerprint: two independent 64-bit lanes, each the sum over all elements of a full-avalanche mix
+// (splitmix64 finaliser) of (index, float bits) under a different key -- a sum so that the grid can accumulate it
+// in any order, a mix keyed on the whole index so that moving, swapping or compensating values cannot cancel.
+// set_dictionary compares both lanes on the device with the previous call's and the table-building kernels below
+// return at once when nothing changed (`skip`): the reference re-derives everything from `d` on every call
+// (modules/matchingpursuit.py:254), and callers that pass an unchanged dictionary again should not pay for it --
+// without a host synchronisation.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
 }
-// fp[0] = fingerprint just accumulated, fp[1] = previous one, fp[2] = previous one is valid
+__global__ void k_fingerprint(const float* __restrict__ d, size_t n, unsigned long long* __restrict__ acc) {
+    unsigned long long s0 = 0, s1 = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned long long e = ((unsigned long long)i << 32) ^ (unsigned long long)(unsigned)__float_as_int(d[i]) ^
+                                     ((unsigned long long)(i >> 32) * 0x9e3779b97f4a7c15ull);
+        s0 += mix64(e + 0x9e3779b97f4a7c15ull);
+        s1 += mix64(~e * 0xd6e8feb86659fd93ull + 0x2545f4914f6cdd1dull);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(acc, s0);
+        atomicAdd(acc + 1, s1);
+    }
+}
+// fp[0..1] = fingerprint just accumulated, fp[2..3] = previous one, fp[4] = previous one is valid
 __global__ void k_fingerprint_decide(unsigned long long* fp, int* skip, int force) {
-    *skip = (!force && fp[2] == 1ull && fp[0] == fp[1]) ? 1 : 0;
-    fp[1] = fp[0];
+    *skip = (!force && fp[4] == 1ull && fp[0] == fp[2] && fp[1] == fp[3]) ? 1 : 0;
+    fp[2] = fp[0];
+    fp[3] = fp[1];
     fp[0] = 0ull;
-    fp[2] = 1ull;
+    fp[1] = 0ull;
+    fp[4] = 1ull;
 }
 
 __global__ void k_unit_norm(const float* __restrict__ x, float* __restrict__ y, int rows, int cols, float eps,
@@ -185,7 +207,7 @@ k_pair_spectra(const float* __restrict__ dict, int A, int atom_lo, int atom_hi,
 // with zeros outside [0, row_len).  win may be indexed indirectly through
 // `nwin_ptr` (device-side count) so the grid can be sized for the worst case.
 // ---------------------------------------------------------------------------
-template <int M>
+template <int M, bool STAGED = false>
 __device__ __forceinline__ void window_fft_body(const float* __restrict__ x, int row_len, int t0, int tl,
                                                 C32* sm, const C32* __restrict__ tw1, const C32* stw2,
                                                 C32* __restrict__ out) {
@@ -202,10 +224,12 @@ __device__ __forceinline__ void window_fft_body(const float* __restrict__ x, int
     __syncthreads();
     F::template pass3<-1>(r, tl, sm);
 #pragma unroll
-    for (int e = 0; e < F::E; ++e) out[F::out_index(tl, e)] = r[e];
+    for (int e = 0; e < F::E; ++e) out[STAGED ? F::bin_addr(F::out_index(tl, e)) : F::out_index(tl, e)] = r[e];
 }
 
-template <int M>
+// STAGED: the spectrum is written in BlockFft's pass-1 shared-memory layout (SMEM_CPX entries per window, bin j at
+// bin_addr(j)) so that a consumer can bulk-copy it into its FFT buffer as it is (k_delta).
+template <int M, bool STAGED = false>
 __global__ void __launch_bounds__(BlockFft<M, float>::T)
 k_window_fft(const float* __restrict__ src, long long row_stride, int row_len, const Win* __restrict__ win,
              const C32* __restrict__ tw1, const C32* __restrict__ tw2, C32* __restrict__ winspec,
@@ -219,8 +243,8 @@ k_window_fft(const float* __restrict__ src, long long row_stride, int row_len, c
     for (int i = tl; i < 256; i += F::T) stw2[i] = tw2[i];
     const Win wi = win[w];
     __syncthreads();
-    window_fft_body<M>(src + (long long)wi.row * row_stride, row_len, wi.t0, tl, sm, tw1, stw2,
-                       winspec + (size_t)w * M);
+    window_fft_body<M, STAGED>(src + (long long)wi.row * row_stride, row_len, wi.t0, tl, sm, tw1, stw2,
+                               winspec + (size_t)w * (STAGED ? F::SMEM_CPX : M));
 }
 
 // ---------------------------------------------------------------------------
@@ -258,6 +282,7 @@ struct CorrArgs {
     long long dense_atom_stride;  // between atoms
     int dense_col_off;            // column = t0 + m + dense_col_off
     const int* skip;              // optional device flag: nothing to do (unchanged dictionary, Gram build)
+    int pos_free;                 // ROWMAX: the tables carry no exact positions (SGRAM, see k_delta NOPOS)
 };
 
 // Shared memory: [tw2: 256 complex][per transform: FFT buffer SMEM_CPX complex][per transform, only
@@ -436,7 +461,8 @@ k_corr(const CorrArgs a) {
                     if (old_ok) {
                         if (lane == 31) take_better(v, at, old_v, old_p);   // nvb <= 22 < 32: lane 31 is free
                     } else {
-                        rescan_row(a.bm_val + o, a.bm_pos + o, a.NB, wi.blk0, wi.nvb, lane, v, at);
+                        rescan_row(a.bm_val + o, a.pos_free ? nullptr : a.bm_pos + o, a.NB, wi.blk0, wi.nvb, lane, v, at,
+                                   a.blk_shift);
                     }
                     warp_argmax(v, at);
                     if (lane == 0) {
@@ -521,11 +547,32 @@ __device__ __forceinline__ Best block_best(const float* __restrict__ row_val, co
     return *s_best;
 }
 
+// Position-free tables (SGRAM, k_delta NOPOS): w.position is only known to lie inside the lowest block of the row
+// that holds the row maximum; the exact winner is the first position of that block whose map value equals it.
+// Called by a whole CTA; every thread returns the resolved record.
+__device__ __forceinline__ Best resolve_position(const float* __restrict__ map_row, int N, int blk_shift, Best w) {
+    __shared__ int s_first[32];
+    const int t0 = (max(w.position, 0) >> blk_shift) << blk_shift;
+    const int t1 = min(t0 + (1 << blk_shift), N);
+    int cand = INT_MAX;
+    for (int t = t0 + (int)threadIdx.x; t < t1; t += blockDim.x)
+        if (map_row[t] + 0.0f == w.value) cand = min(cand, t);
+    cand = __reduce_min_sync(0xffffffffu, cand);
+    if ((threadIdx.x & 31) == 0) s_first[threadIdx.x >> 5] = cand;
+    __syncthreads();
+    cand = INT_MAX;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) cand = min(cand, s_first[i]);
+    __syncthreads();
+    if (cand != INT_MAX) w.position = cand;     // nothing equal (NaN / -inf rows): keep the block start
+    return w;
+}
+
 __global__ void __launch_bounds__(256)
 k_local_best(const float* __restrict__ row_val, const int* __restrict__ row_pos, int nloc, int atom_lo,
-             Best* __restrict__ best) {
+             Best* __restrict__ best, const float* __restrict__ map = nullptr, int NS = 0, int N = 0, int blk_shift = 0) {
     __shared__ Best s_best;
-    const Best r = block_best(row_val, row_pos, blockIdx.x, nloc, atom_lo, &s_best);
+    Best r = block_best(row_val, row_pos, blockIdx.x, nloc, atom_lo, &s_best);
+    if (map) r = resolve_position(map + ((size_t)blockIdx.x * nloc + (r.atom - atom_lo)) * NS, N, blk_shift, r);
     if (threadIdx.x == 0) best[blockIdx.x] = r;
 }
 
@@ -581,6 +628,8 @@ struct ApplyArgs {
     int world, rank, mail_batch;
     unsigned seq;                 // sequence number of this exchange (never 0)
     int* xerr;                    // set when a record did not arrive in time
+    const float* map;             // position-free tables (SGRAM): resident map (B, nloc, NS) the winner's exact position
+    int NS;                       // is resolved from; null otherwise
 };
 
 __device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
@@ -658,6 +707,7 @@ k_apply(const ApplyArgs a) {
     Best w;
     if constexpr (SELECT) {
         w = block_best(a.row_val, a.row_pos, b, a.nloc, a.atom_lo, &s_best);
+        if (a.map) w = resolve_position(a.map + ((size_t)b * a.nloc + (w.atom - a.atom_lo)) * a.NS, a.N, a.blk_shift, w);
         if (a.world > 1) {
             __shared__ Best s_slot[64];
             w = exchange_best(a, b, w, s_slot);
@@ -934,7 +984,8 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // Persistent grid (occupancy x SM count CTAs); work items are (pair group, signal) in pair-major order.
 // ---------------------------------------------------------------------------
 struct DeltaArgs {
-    const C32* atomspec;    // (K, M2): forward spectrum of [0^(A-1), d_k]
+    const C32* atomspec;    // (K, spec_stride): forward spectrum of [0^(A-1), d_k]; MPB_DELTA_SPREF: in BlockFft's
+                            // staged layout (spec_stride = SMEM_CPX), else natural order (spec_stride = M2)
     const C32* pairspec2;   // (npairs, M2): inverse-kernel spectrum of d[2q] + i d[2q+1], scaled 1/M2
     const GramUpdate* upd;  // (B)
     int batch, npairs, nloc;
@@ -953,6 +1004,17 @@ struct DeltaArgs {
 #ifndef MPB_DELTA_MINB
 #define MPB_DELTA_MINB 3
 #endif
+#ifndef MPB_DELTA_NOPOS
+#define MPB_DELTA_NOPOS 1      // position-free block/row tables in SGRAM mode (see k_delta's NOPOS)
+#endif
+#ifndef MPB_DELTA_NOPOS_MIN_ITEMS
+#define MPB_DELTA_NOPOS_MIN_ITEMS 16384
+#endif
+#ifndef MPB_DELTA_SPREF
+#define MPB_DELTA_SPREF 1      // the next item's winner spectrum is bulk-copied (TMA) into the idle FFT buffer while the
+                               // block/row maxima of the current item are reduced; the product phase then reads it from
+                               // shared memory instead of L2
+#endif
 #ifndef MPB_DELTA_E
 #define MPB_DELTA_E 0          // complex values per thread of k_delta's transform (0: BlockFft's default, 16 up to 4096 points)
 #endif
@@ -967,7 +1029,10 @@ struct DeltaCfg {
     using F = BlockFft<M2, float, delta_elems(M2, MPB_DELTA_E)>;
     static constexpr int TPB = F::T < MPB_DELTA_TPB ? MPB_DELTA_TPB : F::T;
 };
-template <int M2>
+// NOPOS: the block and row tables carry no exact positions -- a candidate's "position" is the start of its block
+// (blocks order like positions, so ties resolve alike) and k_apply finds the first position of the maximum inside
+// that block of the resident map.  Saves the position half of every block reduction (whole blocks of 128/256).
+template <int M2, bool NOPOS>
 __global__ void __launch_bounds__(DeltaCfg<M2>::TPB, MPB_DELTA_MINB)
 k_delta(const DeltaArgs a) {
     using F = typename DeltaCfg<M2>::F;
@@ -983,12 +1048,15 @@ k_delta(const DeltaArgs a) {
     float* st0 = reinterpret_cast<float*>(stw2 + 256 + (size_t)NT * F::SMEM_CPX) + (size_t)sb * 2 * a.cap;
     float* st1 = st0 + a.cap;
     __shared__ float2 s_bv_static[NT * 64];
-    __shared__ __align__(8) unsigned long long s_bar[NT];
+    __shared__ __align__(8) unsigned long long s_bar[2 * NT];
     float2* sBV = s_bv_static + sb * 64;                 // [which*32 + block] = (value, position as int bits)
-    unsigned long long* bar = s_bar + sb;
+    unsigned long long* bar = s_bar + sb;                // map window landed
+    unsigned long long* barS = s_bar + NT + sb;          // winner spectrum landed (MPB_DELTA_SPREF)
+    constexpr unsigned SBYTES = (unsigned)(F::SMEM_CPX * sizeof(C32));
     for (int i = threadIdx.x; i < 256; i += TPB) stw2[i] = a.tw2[i];
     if (tl == 0) {
         mbar_init(bar, 1);
+        mbar_init(barS, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
     }
@@ -1009,9 +1077,23 @@ k_delta(const DeltaArgs a) {
         b = (int)(it0 - (long long)g * a.batch);
     }
     C32 r[F::E];
+    unsigned phaseS = 0;
+    // tl == 0: request signal bb's winner spectrum into this transform's (idle) FFT buffer
+    auto request_spectrum = [&](int bb) {
+        const GramUpdate un = a.upd[bb];
+        if (un.valid) {
+            mbar_expect_tx(barS, SBYTES);
+            bulk_load(sm, a.atomspec + (size_t)un.atom * F::SMEM_CPX, SBYTES, barS);
+        }
+    };
+    if (MPB_DELTA_SPREF && tl == 0 && n_items > 0) request_spectrum(b);
     for (; n_items > 0; --n_items, b = (b + 1 == a.batch ? 0 : b + 1), g += (b == 0)) {
-        if (!a.upd[b].valid) continue;                   // CTA-uniform: this signal takes the FFT route
         const GramUpdate u = a.upd[b];
+        const int b_next = (b + 1 == a.batch ? 0 : b + 1);
+        if (!u.valid) {                                  // CTA-uniform: this signal takes the FFT route
+            if (MPB_DELTA_SPREF && tl == 0 && n_items > 1) request_spectrum(b_next);   // nobody touches the buffer now
+            continue;
+        }
         int q = g * NT + sb;
         const bool q_ok = q < a.npairs;
         if (!q_ok) q = a.npairs - 1;
@@ -1049,13 +1131,28 @@ k_delta(const DeltaArgs a) {
             // 5.35 -> 5.99 ms per iteration of 128 signals), and parking the pair spectrum in tensor
             // memory with tcgen05.st/ld.32x32b (correct, but 14.7 ms).
             const C32* __restrict__ Eq = a.pairspec2 + (size_t)q * M2;
-            const C32* __restrict__ S = a.atomspec + (size_t)u.atom * M2;
+            if constexpr (MPB_DELTA_SPREF) {
+                // the pair spectrum comes from L2 while the winner spectrum -- requested during the previous item's
+                // reduction phase -- is read from this thread's own slots of the FFT buffer (the slots pass 1
+                // overwrites below: no barrier needed)
 #pragma unroll
-            for (int e = 0; e < F::E; ++e) {
-                const int j = F::in_index(tl, e);
-                const float2 y = __ldg(reinterpret_cast<const float2*>(Eq + j));
-                const float2 x = __ldg(reinterpret_cast<const float2*>(S + j));
-                r[e] = cmul(C32{x.x, x.y}, C32{y.x, y.y});
+                for (int e = 0; e < F::E; ++e) {
+                    const float2 y = __ldg(reinterpret_cast<const float2*>(Eq + F::in_index(tl, e)));
+                    r[e] = C32{y.x, y.y};
+                }
+                while (!mbar_try_wait(barS, phaseS)) {}
+                phaseS ^= 1u;
+#pragma unroll
+                for (int e = 0; e < F::E; ++e) r[e] = cmul(sm[F::slot_addr(tl, e)], r[e]);
+            } else {
+                const C32* __restrict__ S = a.atomspec + (size_t)u.atom * M2;
+#pragma unroll
+                for (int e = 0; e < F::E; ++e) {
+                    const int j = F::in_index(tl, e);
+                    const float2 y = __ldg(reinterpret_cast<const float2*>(Eq + j));
+                    const float2 x = __ldg(reinterpret_cast<const float2*>(S + j));
+                    r[e] = cmul(C32{x.x, x.y}, C32{y.x, y.y});
+                }
             }
         }
         if constexpr (MPB_TWGEN && F::R1 >= 4) F::template pass1_gen<1>(r, tl, sm, a.tw1);
@@ -1108,14 +1205,16 @@ k_delta(const DeltaArgs a) {
                     }
                 }
             }
-            fence_proxy_async();                         // generic-proxy writes -> visible to the bulk stores
         }
+        fence_proxy_async();                             // generic-proxy writes -> visible to the bulk stores; the FFT
+                                                         // buffer's generic writes are ordered before its bulk refill
         __syncthreads();                                 // rows updated; FFT buffer free
         if (tl == 0 && q_ok) {
             bulk_store(m0, st0, (unsigned)cnt * 4u);
             if (second) bulk_store(m1, st1, (unsigned)cnt * 4u);
             bulk_commit();
         }
+        if (MPB_DELTA_SPREF && tl == 0 && n_items > 1) request_spectrum(b_next);
         if (q_ok) {
             // (row, block) tasks are dealt round-robin to the warps; the refreshed (max, position) pairs
             // only go to shared memory here -- the row warps publish them to bm_val / bm_pos.
@@ -1137,6 +1236,10 @@ k_delta(const DeltaArgs a) {
                     const int kmax = __reduce_max_sync(0xffffffffu, float_key(v));
                     v = __int_as_float(kmax ^ ((kmax >> 31) & 0x7fffffff));
                     if (!(v == v)) v = -INFINITY;                 // a NaN in the map never wins (as in the comparison-based paths)
+                    if constexpr (NOPOS) {
+                        if (lane == 0) sBV[slot] = make_float2(v, __int_as_float(start + ((slot & 31) << sh)));
+                        continue;
+                    }
                     int at = INT_MAX;                             // descending order: the lowest matching position survives
                     at = (c1.w + 0.0f == v) ? 131 : at;
                     at = (c1.z + 0.0f == v) ? 130 : at;
@@ -1220,14 +1323,14 @@ k_delta(const DeltaArgs a) {
                 v = c.x;
                 at = __float_as_int(c.y);
                 a.bm_val[o + blk0 + lane] = v;           // coalesced publication of the refreshed blocks
-                a.bm_pos[o + blk0 + lane] = at;
+                if constexpr (!NOPOS) a.bm_pos[o + blk0 + lane] = at;
             }
             const int old_b = old_p[wi] >> a.blk_shift;
             const bool old_ok = old_b < blk0 || old_b >= blk0 + nvb;
             if (old_ok) {
                 if (lane == 31) take_better(v, at, old_v[wi], old_p[wi]);   // nvb <= 30: lane 31 is free
             } else {
-                rescan_row(a.bm_val + o, a.bm_pos + o, a.NB, blk0, nvb, lane, v, at);
+                rescan_row(a.bm_val + o, NOPOS ? nullptr : a.bm_pos + o, a.NB, blk0, nvb, lane, v, at, a.blk_shift);
             }
             warp_argmax(v, at);
             if (lane == 0) {

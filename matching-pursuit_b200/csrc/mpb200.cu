@@ -81,6 +81,14 @@ int choose_fft_size(int A) {
     return 0;
 }
 
+// Entries per atom of the SGRAM winner spectra: BlockFft<M2>::SMEM_CPX when k_delta bulk-copies them into its FFT
+// buffer (staged layout, MPB_DELTA_SPREF), else M2.
+static size_t spec_stride(int M2) {
+    if (!MPB_DELTA_SPREF) return (size_t)M2;
+    const int R1 = M2 / 256, S = R1 | 1, XS = 16 * S + (R1 < 16 ? R1 : 0);
+    return (size_t)16 * XS;
+}
+
 template <typename Real>
 static void host_twiddles(int M, std::vector<cpx<Real>>& t1, std::vector<cpx<Real>>& t2) {
     const long double two_pi = 6.283185307179586476925286766559005768L;
@@ -127,13 +135,18 @@ static void free_plan(Plan* p) {
 // ---------------------------------------------------------------------------
 static int launch_window_fft_ex(int M, const C32* tw1, const C32* tw2, const float* src, long long row_stride,
                                 int row_len, const Win* win, int nwin, C32* winspec, cudaStream_t st,
-                                const int* skip = nullptr) {
+                                const int* skip = nullptr, bool staged = false) {
     if (nwin <= 0) return MPB200_OK;
     MPB_DISPATCH_M(M, {
         using F = BlockFft<MM, float>;
         const size_t smem = (size_t)(F::SMEM_CPX + 256) * sizeof(C32);
-        MPB_CUDA(allow_smem(k_window_fft<MM>, smem));
-        k_window_fft<MM><<<nwin, F::T, smem, st>>>(src, row_stride, row_len, win, tw1, tw2, winspec, skip);
+        if (staged) {
+            MPB_CUDA((allow_smem(k_window_fft<MM, true>, smem)));
+            k_window_fft<MM, true><<<nwin, F::T, smem, st>>>(src, row_stride, row_len, win, tw1, tw2, winspec, skip);
+        } else {
+            MPB_CUDA((allow_smem(k_window_fft<MM, false>, smem)));
+            k_window_fft<MM, false><<<nwin, F::T, smem, st>>>(src, row_stride, row_len, win, tw1, tw2, winspec, skip);
+        }
     });
     MPB_LAUNCH_CHECK("k_window_fft");
     return MPB200_OK;
@@ -275,6 +288,8 @@ static int launch_apply(Plan* p, int batch, const Best* winner, int step, int n_
     a.upd = p->upd;
     a.trunc_count = p->trunc_count;
     a.parity = (int)(p->iter & 1u);
+    a.map = (SELECT && p->pos_free) ? p->map : nullptr;
+    a.NS = p->NS;
     MPB_DISPATCH_M(p->M, {
         using F = BlockFft<MM, float>;
         const size_t smem = (size_t)(F::SMEM_CPX + 256) * sizeof(C32);
@@ -333,9 +348,10 @@ static int step_refresh(Plan* p, int batch, cudaStream_t st) {
                 constexpr int NT = TPB / F::T;
                 const size_t smem = (size_t)(256 + NT * F::SMEM_CPX) * sizeof(C32) +
                                     (size_t)NT * 2 * d.cap * sizeof(float);
-                MPB_CUDA(allow_smem(k_delta<MM>, smem));
+                auto kernel = p->pos_free ? k_delta<MM, true> : k_delta<MM, false>;
+                MPB_CUDA(allow_smem(kernel, smem));
                 if (p->delta_occ == 0) {
-                    MPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->delta_occ, k_delta<MM>, TPB, smem));
+                    MPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->delta_occ, kernel, TPB, smem));
                     if (p->delta_occ < 1) p->delta_occ = 1;
                 }
                 d.ngroups = (p->npairs + NT - 1) / NT;
@@ -343,7 +359,7 @@ static int step_refresh(Plan* p, int batch, cudaStream_t st) {
                 if (items >= (1LL << 31)) return fail(MPB200_EINVAL, "SGRAM: more than 2^31 (pair, signal) work items per launch");
                 long long ctas = (long long)p->sm_count * p->delta_occ;
                 if (ctas > items) ctas = items;
-                k_delta<MM><<<(unsigned)ctas, TPB, smem, st>>>(d);
+                kernel<<<(unsigned)ctas, TPB, smem, st>>>(d);
             });
             MPB_LAUNCH_CHECK("k_delta");
             mark(p, 4, st);
@@ -355,6 +371,7 @@ static int step_refresh(Plan* p, int batch, cudaStream_t st) {
             a.dense_row_stride = (long long)p->nloc * p->NS;
             a.dense_atom_stride = p->NS;
             a.dense_col_off = 0;
+            a.pos_free = p->pos_free ? 1 : 0;
             rc = launch_corr<MODE_DENSE | MODE_BLOCKMAX | MODE_ROWMAX>(p, a, trunc_groups(p, batch), st);
         }
     } else if (p->mode == MPB200_MODE_GRAM) {
@@ -453,7 +470,7 @@ static int build_sgram_tables(Plan* p, cudaStream_t st) {
     });
     MPB_LAUNCH_CHECK("k_pair_spectra");
     return launch_window_fft_ex(p->M2, p->tw1b, p->tw2, p->dict, p->A, p->A, p->win_atoms, p->K, p->atomspec, st,
-                                p->dict_skip);
+                                p->dict_skip, MPB_DELTA_SPREF != 0);
 }
 
 // With CUDA's lazy module loading the FIRST use of a kernel may synchronise the context.  A pursuit whose
@@ -468,7 +485,7 @@ static int preload_kernels(Plan* p) {
     MPB_DISPATCH_M(p->M, {
         touch(k_apply<MM, true>);
         touch(k_apply<MM, false>);
-        touch(k_window_fft<MM>);
+        touch(k_window_fft<MM, false>);
         touch(k_corr<MM, MODE_BLOCKMAX>);
         touch(k_corr<MM, MODE_DENSE>);
         touch(k_corr<MM, MODE_DENSE | MODE_BLOCKMAX>);
@@ -476,7 +493,7 @@ static int preload_kernels(Plan* p) {
         touch(k_corr<MM, MODE_DENSE | MODE_BLOCKMAX | MODE_ROWMAX>);
     });
     if (p->mode == MPB200_MODE_SGRAM) {
-        MPB_DISPATCH_M(p->M2, { touch(k_delta<MM>); });
+        MPB_DISPATCH_M(p->M2, { touch(k_delta<MM, true>); touch(k_delta<MM, false>); touch(k_window_fft<MM, true>); });
     }
     touch(k_gram_update<16>);
     touch(k_gram_update<32>);
@@ -486,6 +503,35 @@ static int preload_kernels(Plan* p) {
     touch(k_rowmax);
     touch(k_local_best);
     touch(k_reduce_best);
+    return MPB200_OK;
+}
+
+// Device staging of the host-buffer entry point (mpb200_sparse_code_host): the signals of a whole batch and
+// (atom, position, value) for `steps` iterations of every signal.  Sized at plan creation for
+// MPB200_DEFAULT_MAX_STEPS iterations; MPB200_OPT_MAX_STEPS re-sizes it ahead of time.  A call that needs more
+// re-sizes it on the spot (the one allocation the library makes after plan creation, like a vector that grows);
+// the outgrown buffers are released at once.
+static int reserve_host_staging(Plan* p, size_t steps) {
+    const size_t ev = (size_t)p->Bmax * steps;
+    if (p->d_signal && ev <= p->ev_cap) return MPB200_OK;
+    if (p->d_atom) {
+        MPB_CUDA(cudaDeviceSynchronize());
+        for (void* q : {(void*)p->d_atom, (void*)p->d_pos, (void*)p->d_val}) {
+            cudaFree(q);
+            for (auto it = p->allocs.begin(); it != p->allocs.end(); ++it)
+                if (*it == q) { p->allocs.erase(it); break; }
+        }
+        p->bytes -= p->ev_cap * 12;
+        p->d_atom = nullptr; p->d_pos = nullptr; p->d_val = nullptr;
+        p->ev_cap = 0;
+    }
+    int rc = MPB200_OK;
+    if (!p->d_signal) rc = dev_alloc(p, &p->d_signal, (size_t)p->Bmax * p->N);
+    if (!rc) rc = dev_alloc(p, &p->d_atom, ev);
+    if (!rc) rc = dev_alloc(p, &p->d_pos, ev);
+    if (!rc) rc = dev_alloc(p, &p->d_val, ev);
+    if (rc) return rc;
+    p->ev_cap = ev;
     return MPB200_OK;
 }
 
@@ -565,7 +611,7 @@ int mpb200_plan_create(mpb200_plan_t* out, int n_atoms, int atom_size, int n_sam
     // per-signal bytes of the structures every mode keeps + the resident map
     const uint64_t per_signal = map_row_bytes + (uint64_t)p->nloc * p->NB * 8 + (uint64_t)p->nloc * 8 +
                                 (uint64_t)n_samples * 4;
-    const uint64_t sgram_fixed = (uint64_t)n_atoms * M2 * 8 + (uint64_t)p->npairs * (M2 + M) * 8 +
+    const uint64_t sgram_fixed = (uint64_t)n_atoms * spec_stride(M2) * 8 + (uint64_t)p->npairs * (M2 + M) * 8 +
                                  (uint64_t)2048 * M * 8 + (uint64_t)n_atoms * atom_size * 4;
     long long cap = (long long)(((double)free_b * 0.85 - (double)sgram_fixed) / (double)per_signal);
     if (mode == MPB200_MODE_SGRAM && gram_budget_bytes) {   // explicit cap on the resident map
@@ -606,6 +652,9 @@ int mpb200_plan_create(mpb200_plan_t* out, int n_atoms, int atom_size, int n_sam
         const long long n_sub = (max_batch + cap - 1) / cap;         // balanced sub-batches
         p->Bcap = (int)((max_batch + n_sub - 1) / n_sub);
         p->NS = ns_pad;
+        // position-free block tables pay when the refresh kernel dominates (k_apply then resolves the winner's
+        // exact position with one extra dependent load); latency-bound shapes keep exact positions
+        p->pos_free = MPB_DELTA_NOPOS && p->blk >= 128 && (long long)p->Bcap * p->npairs >= MPB_DELTA_NOPOS_MIN_ITEMS;
     }
     const int alloc_batch = p->Bcap;
 
@@ -643,7 +692,7 @@ int mpb200_plan_create(mpb200_plan_t* out, int n_atoms, int atom_size, int n_sam
     MPB_TRY(dev_alloc(p, &p->row_pos, (size_t)alloc_batch * p->nloc));
     MPB_TRY(dev_alloc(p, &p->residual, (size_t)alloc_batch * n_samples));
     MPB_TRY(dev_alloc(p, &p->best, (size_t)alloc_batch));
-    MPB_TRY(dev_alloc(p, &p->fp, (size_t)3));
+    MPB_TRY(dev_alloc(p, &p->fp, (size_t)5));
     MPB_TRY(dev_alloc(p, &p->dict_skip, (size_t)1));
     std::vector<Win> wg;
     if (mode == MPB200_MODE_GRAM) {
@@ -672,7 +721,7 @@ int mpb200_plan_create(mpb200_plan_t* out, int n_atoms, int atom_size, int n_sam
         MPB_TRY(dev_alloc(p, &p->upd, (size_t)alloc_batch));
         MPB_TRY(dev_alloc(p, &p->trunc_count, (size_t)2));
         MPB_TRY(dev_alloc(p, &p->pairspec2, (size_t)p->npairs * M2));
-        MPB_TRY(dev_alloc(p, &p->atomspec, (size_t)n_atoms * M2));
+        MPB_TRY(dev_alloc(p, &p->atomspec, (size_t)n_atoms * spec_stride(M2)));
         MPB_TRY(dev_alloc(p, &p->tw1b, (size_t)M2));
         MPB_TRY(dev_alloc(p, &p->tw1bd, (size_t)M2));
         MPB_TRY(dev_alloc(p, &p->win_atoms, (size_t)n_atoms));
@@ -702,12 +751,16 @@ int mpb200_plan_create(mpb200_plan_t* out, int n_atoms, int atom_size, int n_sam
         up(p->tw1b, t1b.data(), t1b.size() * sizeof(t1b[0]));
         up(p->tw1bd, t1bd.data(), t1bd.size() * sizeof(t1bd[0]));
     }
-    if (e == cudaSuccess) e = cudaMemset(p->fp, 0, 3 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(p->fp, 0, 5 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(p->dict_skip, 0, sizeof(int));
     if (p->gram && e == cudaSuccess) e = cudaMemset(p->gram, 0, (size_t)n_atoms * p->nloc * p->GS * sizeof(float));
     if (e != cudaSuccess) {
         free_plan(p);
         return fail(MPB200_ECUDA, std::string("table upload: ") + cudaGetErrorString(e));
+    }
+    {
+        const int rs = reserve_host_staging(p, MPB200_DEFAULT_MAX_STEPS);
+        if (rs) { free_plan(p); return rs; }
     }
     *out = reinterpret_cast<mpb200_plan_t>(p);
     return MPB200_OK;
@@ -782,8 +835,10 @@ static int set_dictionary_impl(mpb200_plan_t plan, const float* d, bool normaliz
     if (fgrid > p->sm_count * 8) fgrid = p->sm_count * 8;
     k_fingerprint<<<fgrid, 256, 0, st>>>(d, n_dict, p->fp);
     MPB_LAUNCH_CHECK("k_fingerprint");
-    k_fingerprint_decide<<<1, 1, 0, st>>>(p->fp, p->dict_skip, (!p->dict_set || p->last_normalize != (int)normalize) ? 1 : 0);
+    k_fingerprint_decide<<<1, 1, 0, st>>>(p->fp, p->dict_skip,
+                                          (!p->dict_set || p->force_tables || p->last_normalize != (int)normalize) ? 1 : 0);
     MPB_LAUNCH_CHECK("k_fingerprint_decide");
+    p->force_tables = false;
     p->last_normalize = (int)normalize;
     if (normalize) {
         k_unit_norm<<<(p->K + 7) / 8, 256, 0, st>>>(d, p->dict, p->K, p->A, 1e-8f, p->dict_skip);
@@ -814,6 +869,15 @@ int mpb200_plan_set_option(mpb200_plan_t plan, int option, long long value) {
             if (value < 0) return fail(MPB200_EINVAL, "refresh_every must be >= 0");
             p->refresh_every = (int)value;
             return MPB200_OK;
+        case MPB200_OPT_FORCE_TABLES:
+            p->force_tables = value != 0;
+            return MPB200_OK;
+        case MPB200_OPT_MAX_STEPS: {
+            if (value < 1) return fail(MPB200_EINVAL, "max_steps must be >= 1");
+            int rc = check_plan(p, false);
+            if (rc) return rc;
+            return reserve_host_staging(p, (size_t)value);
+        }
         default:
             return fail(MPB200_EINVAL, "unknown option");
     }
@@ -861,7 +925,8 @@ int mpb200_local_best(mpb200_plan_t plan, mpb200_best* best, void* stream) {
     if (rc) return rc;
     if (p->cur_batch < 1) return fail(MPB200_ESTATE, "mpb200_begin has not been called");
     k_local_best<<<p->cur_batch, 256, 0, (cudaStream_t)stream>>>(p->row_val, p->row_pos, p->nloc, p->lo,
-                                                                  reinterpret_cast<Best*>(best));
+                                                                  reinterpret_cast<Best*>(best),
+                                                                  p->pos_free ? p->map : nullptr, p->NS, p->N, p->blk_shift);
     MPB_LAUNCH_CHECK("k_local_best");
     return MPB200_OK;
 }
@@ -1042,6 +1107,17 @@ int mpb200_exchange_status(mpb200_plan_t plan, int* timed_out) {
     return MPB200_OK;
 }
 
+int mpb200_exchange_disconnect(mpb200_plan_t plan) {
+    Plan* p = reinterpret_cast<Plan*>(plan);
+    int rc = check_plan(p, false);
+    if (rc) return rc;
+    MPB_CUDA(cudaDeviceSynchronize());
+    for (void* m : p->ipc_opened) cudaIpcCloseMemHandle(m);
+    p->ipc_opened.clear();
+    p->xconnected = false;
+    return MPB200_OK;
+}
+
 int mpb200_sparse_code_host(mpb200_plan_t plan, const float* signal_host, int batch, int n_steps,
                             float* residual_out_host, int32_t* atom_out_host, int32_t* pos_out_host,
                             float* val_out_host, void* stream) {
@@ -1053,17 +1129,9 @@ int mpb200_sparse_code_host(mpb200_plan_t plan, const float* signal_host, int ba
     cudaStream_t st = (cudaStream_t)stream;
     const size_t sig_bytes = (size_t)batch * p->N * sizeof(float);
     const size_t ev = (size_t)batch * (size_t)n_steps;
-    if (!p->d_signal) {
-        rc = dev_alloc(p, &p->d_signal, (size_t)p->Bmax * p->N);
+    if (!p->d_signal || (size_t)p->Bmax * (size_t)n_steps > p->ev_cap) {
+        rc = reserve_host_staging(p, (size_t)(n_steps > 0 ? n_steps : 1));     // beyond the reserved iteration count
         if (rc) return rc;
-    }
-    if (ev > p->ev_cap) {
-        // event staging grows with n_steps; old buffers stay owned by the plan until destroy
-        rc = dev_alloc(p, &p->d_atom, ev);
-        if (!rc) rc = dev_alloc(p, &p->d_pos, ev);
-        if (!rc) rc = dev_alloc(p, &p->d_val, ev);
-        if (rc) return rc;
-        p->ev_cap = ev;
     }
     MPB_CUDA(cudaMemcpyAsync(p->d_signal, signal_host, sig_bytes, cudaMemcpyHostToDevice, st));
     // the residual overwrites the staged signal (a sub-batch's input is consumed before its residual is stored)
@@ -1099,40 +1167,28 @@ int mpb200_correlate(mpb200_plan_t plan, const float* signal, int batch, float* 
     return MPB200_OK;
 }
 
-// Scratch for k_select_dense partial winners: one growing buffer per device (never shrinks;
-// stream-ordered reuse is safe because consecutive calls on different streams are the
-// caller's to order, as with any workspace-free entry point).
-static Best* g_sel_scratch[64] = {nullptr};
-static size_t g_sel_cap[64] = {0};
-
+// Scratch for k_select_dense's partial winners: a stream-ordered allocation (cudaMallocAsync / cudaFreeAsync on
+// the caller's stream), so the entry point keeps no state between calls and concurrent streams never share it.
 static int select_dense_impl(const float* fm, int batch, int n_atoms, int n_samples, int atom_offset,
                              mpb200_best* best, bool lcn, void* stream) {
     if (!fm || !best || batch < 1 || n_atoms < 1 || n_samples < 1) return fail(MPB200_EINVAL, "bad argument");
     int dev = 0;
     MPB_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) return fail(MPB200_EINVAL, "device index out of range");
     int sms = 148;
     MPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int G = (sms * 8 + batch - 1) / batch;   // CTAs per signal: fill the chip ~8 deep
     if (G > n_atoms) G = n_atoms;
     if (G < 1) G = 1;
     const size_t need = (size_t)G * batch;
-    if (need > g_sel_cap[dev]) {
-        if (g_sel_scratch[dev]) {
-            MPB_CUDA(cudaDeviceSynchronize());
-            cudaFree(g_sel_scratch[dev]);
-            g_sel_scratch[dev] = nullptr;
-            g_sel_cap[dev] = 0;
-        }
-        cudaError_t e = cudaMalloc((void**)&g_sel_scratch[dev], need * sizeof(Best));
+    cudaStream_t st = (cudaStream_t)stream;
+    Best* part = nullptr;
+    {
+        cudaError_t e = cudaMallocAsync((void**)&part, need * sizeof(Best), st);
         if (e != cudaSuccess) {
             cudaGetLastError();
             return fail(MPB200_ENOMEM, std::string("select scratch: ") + cudaGetErrorString(e));
         }
-        g_sel_cap[dev] = need;
     }
-    cudaStream_t st = (cudaStream_t)stream;
-    Best* part = g_sel_scratch[dev];
     if (lcn) k_select_dense<true><<<dim3(G, batch), 256, 0, st>>>(fm, n_atoms, n_samples, atom_offset, part);
     else k_select_dense<false><<<dim3(G, batch), 256, 0, st>>>(fm, n_atoms, n_samples, atom_offset, part);
     MPB_LAUNCH_CHECK("k_select_dense");
@@ -1141,6 +1197,7 @@ static int select_dense_impl(const float* fm, int batch, int n_atoms, int n_samp
     k_finish_best<<<(batch + 127) / 128, 128, 0, st>>>(reinterpret_cast<Best*>(best), batch, fm, n_atoms, n_samples,
                                                        atom_offset);
     MPB_LAUNCH_CHECK("k_finish_best");
+    MPB_CUDA(cudaFreeAsync(part, st));
     return MPB200_OK;
 }
 

@@ -20,6 +20,8 @@ struct Plan {
     int NS = 0;                                     // row stride of the resident map (N, or N padded to 4 in SGRAM)
     int delta_occ = 0;                              // SGRAM: resident CTAs per SM of k_delta (persistent grid)
     int M2 = 0;                                     // SGRAM: transform length of the synthesised Gram rows (>= 2A)
+    bool pos_free = false;                          // SGRAM with blocks of >= 128 positions: the block/row tables carry block
+                                                    // starts instead of exact positions (k_delta NOPOS); k_apply resolves
     int wcap = 0;                                   // window-spectrum slots
     int bm_cap = 0;                                 // positions refreshed by one step window (staging size)
     int cur_batch = 0;                              // batch loaded by mpb200_begin (0 = none)
@@ -65,9 +67,10 @@ struct Plan {
     bool xconnected = false;
 
     // unchanged-dictionary detection (device side, no host synchronisation)
-    unsigned long long* fp = nullptr;       // [0] fingerprint being accumulated, [1] previous, [2] previous valid
+    unsigned long long* fp = nullptr;       // [0..1] fingerprint being accumulated, [2..3] previous, [4] previous valid
     int* dict_skip = nullptr;               // device flag read by the table-building kernels
     int last_normalize = -1;
+    bool force_tables = false;              // MPB200_OPT_FORCE_TABLES: the next set_dictionary rebuilds whatever the fingerprint says
 
     // staging for the host-buffer entry point
     float* d_signal = nullptr;

@@ -124,6 +124,17 @@ class AtomShardedPursuit:
         self.engine.set_dictionary(d)
         return self
 
+    def close(self) -> None:
+        """Collective teardown: every rank unmaps its peers' mailboxes BEFORE any rank frees its own (freeing
+        memory that another process still has mapped through CUDA IPC is undefined)."""
+        plan = getattr(self.engine, "plan", None)
+        if plan is None:
+            return
+        if self.exchange == "p2p" and self.world > 1:
+            plan.exchange_disconnect()
+            dist.barrier(group=self.group)
+        plan.close()
+
     def _exchange(self, local: torch.Tensor) -> torch.Tensor:
         """All-gather of the (B, 4) int32 records -> rank-major (world*B, 4)."""
         if self.world == 1:

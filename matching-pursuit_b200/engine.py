@@ -53,12 +53,14 @@ class Plan:
         self.device = _require_cuda(device)
         self._lib = lib()
         lo, hi = (0, n_atoms) if atom_range is None else atom_range
-        self._h = C.c_void_p()
+        handle = C.c_void_p()
         with torch.cuda.device(self.device):
-            check(self._lib.mpb200_plan_create(C.byref(self._h), n_atoms, atom_size, n_samples, max_batch,
+            check(self._lib.mpb200_plan_create(C.byref(handle), n_atoms, atom_size, n_samples, max_batch,
                                                MODES[mode] if isinstance(mode, str) else int(mode), lo, hi,
                                                C.c_uint64(gram_budget_bytes)), "mpb200_plan_create")
-        self._finalizer = weakref.finalize(self, Plan._destroy, self._lib, self._h)
+        self._handle = handle
+        self.pins = 0                # users that hold the plan across calls (plan caches must not close a pinned plan)
+        self._finalizer = weakref.finalize(self, Plan._destroy, self._lib, handle)
         info = PlanInfo()
         check(self._lib.mpb200_plan_info_get(self._h, C.byref(info)), "mpb200_plan_info_get")
         self.info = info
@@ -77,8 +79,28 @@ class Plan:
         if handle:
             library.mpb200_plan_destroy(handle)
 
+    @property
+    def _h(self):
+        """The native handle; a closed plan raises instead of handing freed memory to the library."""
+        if self._handle is None:
+            raise MpbError("this plan has been closed (mpb200_plan_destroy has run); create a new one")
+        return self._handle
+
+    @property
+    def closed(self) -> bool:
+        return self._handle is None
+
     def close(self):
         self._finalizer()
+        self._handle = None
+
+    def __enter__(self):
+        self.pins += 1
+        return self
+
+    def __exit__(self, *exc):
+        self.pins -= 1
+        return False
 
     def set_refresh_every(self, iterations: int) -> "Plan":
         """GRAM mode: re-correlate the whole map every ``iterations`` steps (0 = never)."""
@@ -219,6 +241,11 @@ class Plan:
         arr = (C.c_void_p * len(mailboxes))(*mailboxes)
         with torch.cuda.device(self.device):
             check(self._lib.mpb200_exchange_connect_local(self._h, arr), "mpb200_exchange_connect_local")
+
+    def exchange_disconnect(self) -> None:
+        """Unmap the peers' mailboxes (collective teardown, see distributed.AtomShardedPursuit.close)."""
+        with torch.cuda.device(self.device):
+            check(self._lib.mpb200_exchange_disconnect(self._h), "mpb200_exchange_disconnect")
 
     def exchange_timed_out(self) -> bool:
         flag = C.c_int(0)

@@ -38,18 +38,32 @@ _PLAN_CACHE_FRACTION = 0.25      # of the device memory: older plans are closed 
 
 
 def _evict_until(dev_index: int, max_bytes: int, max_entries: int) -> None:
-    def held():
-        return sum(p.device_bytes for key, p in _PLAN_CACHE.items() if key[0] == dev_index)
-    while _PLAN_CACHE and (len(_PLAN_CACHE) > max_entries or held() > max_bytes):
-        _PLAN_CACHE.pop(next(iter(_PLAN_CACHE))).close()          # oldest first (dicts keep insertion order)
+    """Close this device's oldest idle plans until it holds at most `max_bytes` in at most `max_entries` cached
+    plans.  A plan that somebody is using (``with plan:``, see :func:`_run`) is never closed, and other devices'
+    plans are neither counted nor touched."""
+    def mine():
+        return [(key, p) for key, p in _PLAN_CACHE.items() if key[0] == dev_index]     # oldest first (insertion order)
+
+    def over():
+        held = mine()
+        return len(held) > max_entries or sum(p.device_bytes for _, p in held) > max_bytes
+    while over():
+        idle = [key for key, p in mine() if p.pins == 0]
+        if not idle:
+            break
+        _PLAN_CACHE.pop(idle[0]).close()
 
 
 def get_plan(n_atoms: int, atom_size: int, n_samples: int, batch: int, device, mode: str = "auto") -> Plan:
+    """A cached plan for this shape (most recently used last).  Callers that keep the plan across further
+    ``get_plan`` calls hold it with ``with plan:`` so that making room for another plan cannot close it."""
     dev = engine._require_cuda(device)
     key = (dev.index, n_atoms, atom_size, n_samples, mode)
     plan = _PLAN_CACHE.pop(key, None)
-    if plan is not None and plan.max_batch < batch:
+    if plan is not None and (plan.closed or (plan.max_batch < batch and plan.pins == 0)):
         plan.close()
+        plan = None
+    if plan is not None and plan.max_batch < batch:               # too small but in use: leave it to its user
         plan = None
     if plan is None:
         total = torch.cuda.get_device_properties(dev).total_memory
@@ -57,15 +71,16 @@ def get_plan(n_atoms: int, atom_size: int, n_samples: int, batch: int, device, m
         try:
             plan = Plan(n_atoms, atom_size, n_samples, batch, mode=mode, device=dev)
         except MpbError:
-            clear_plan_cache()                                    # make room and try once more
+            clear_plan_cache(dev.index)                           # make room (idle plans only) and try once more
             plan = Plan(n_atoms, atom_size, n_samples, batch, mode=mode, device=dev)
     _PLAN_CACHE[key] = plan                                       # (re)inserted last: most recently used
     return plan
 
 
-def clear_plan_cache() -> None:
-    while _PLAN_CACHE:
-        _PLAN_CACHE.popitem()[1].close()
+def clear_plan_cache(dev_index: Optional[int] = None) -> None:
+    """Close every idle cached plan (of one device, or of all)."""
+    for key in [k for k, p in _PLAN_CACHE.items() if (dev_index is None or k[0] == dev_index) and p.pins == 0]:
+        _PLAN_CACHE.pop(key).close()
 
 
 def _work_device(signal: torch.Tensor, device=None) -> torch.device:
@@ -234,13 +249,23 @@ def _run(signal: torch.Tensor, d: torch.Tensor, n_steps: int, device, approx, mo
     k, a = d.shape[0], d.shape[-1]
     work = plan.device if plan is not None else _work_device(signal, device)
     sig2d = engine._dev_f32(signal, work, (b, n))
-    if plan is None:
-        plan = get_plan(k, a, n, b, work, mode)
-        plan.set_dictionary(d)
     if isinstance(approx, int) and not isinstance(approx, bool) and approx < n:
         raise NotImplementedError(
             "approx=int<N (top-k spectral bins, modules/conv.py:30-47) is defective in the reference (only atom 0 "
             "is populated) and is not part of the engine; pass approx=None, a slice, or approx>=n_samples")
+    if plan is None:
+        # the dense schedule (per-step callbacks, LCN, band-limited maps) only ever calls correlate(): a
+        # re-correlation plan holds no resident map or Gram table that would go unused
+        dense_path = dense_kwargs is not None or isinstance(approx, slice)
+        plan = get_plan(k, a, n, b, work, "recorrelate" if (dense_path and mode == "auto") else mode)
+        plan.set_dictionary(d)
+    with plan:                       # held: further get_plan calls (below, or inside callbacks) must not evict it
+        return _run_held(plan, sig2d, d, n_steps, approx, dense_kwargs, work)
+
+
+def _run_held(plan: Plan, sig2d: torch.Tensor, d: torch.Tensor, n_steps: int, approx, dense_kwargs, work):
+    b, n = sig2d.shape
+    k, a = d.shape[0], d.shape[-1]
     if isinstance(approx, slice):
         # band-limited correlation (modules/conv.py:24-29): the mask acts on the whole length-(N+A) spectrum of
         # the residual, so every step changes the whole map -- the reference's recompute-per-step schedule it is
@@ -253,6 +278,9 @@ def _run(signal: torch.Tensor, d: torch.Tensor, n_steps: int, device, approx, mo
             plan_long.set_dictionary(d)
             dense_kwargs["compute_feature_map"] = \
                 lambda residual, du: band_limited_map(residual.view(b, n), plan_long, n, approx)
+            with plan_long:
+                atom, pos, val, residual, du = _pursuit_dense(sig2d, plan, n_steps, **dense_kwargs)
+            return plan, atom, pos, val, residual, du, work
     if dense_kwargs is not None:
         atom, pos, val, residual, du = _pursuit_dense(sig2d, plan, n_steps, **dense_kwargs)
     else:

@@ -29,11 +29,11 @@ def run_sparse_code(ref, signal, d, steps, **kw):
     def visit(fm, ai, p, a):
         top2 = torch.topk(fm.reshape(-1).double(), 2)[0]
         margin = float((top2[0] - top2[1]) / top2[0].abs().clamp_min(1e-300))
-        seq.append((ai, int(p), float(a.norm()), margin))
+        seq.append((ai, int(p), float(a.norm()), margin, float(fm[ai, int(p)])))
 
     flat, scatter, residual = ref.matchingpursuit.sparse_code(
         signal, d, n_steps=steps, flatten=True, return_residual=True, visit_key_point=visit, **kw)
-    seq = np.array(seq, dtype=np.float64).reshape(steps, b, 4)
+    seq = np.array(seq, dtype=np.float64).reshape(steps, b, 5)
     # value of each event = <scaled atom, unit atom>; recover it signed from the returned atoms
     du = ref.normalization.unit_norm(d)
     order = np.array([(ai, j, int(p)) for ai, j, p, a in flat], dtype=np.int64)
@@ -41,7 +41,7 @@ def run_sparse_code(ref, signal, d, steps, **kw):
     recon = scatter(tuple(signal.shape), flat)
     return dict(signal=signal.numpy(), d=d.numpy(), steps=np.int64(steps),
                 atom=seq[..., 0].astype(np.int64), pos=seq[..., 1].astype(np.int64),
-                absval=seq[..., 2].astype(np.float32), margin=seq[..., 3],
+                absval=seq[..., 2].astype(np.float32), margin=seq[..., 3], val=seq[..., 4].astype(np.float32),
                 flat_order=order, flat_val=flat_val.astype(np.float32),
                 residual=residual.detach().numpy(), recon=recon.detach().numpy())
 

@@ -44,8 +44,14 @@ def test_binding_covers_every_declared_symbol():
 
 
 def test_version(library):
+    """Header, library and binding agree on the ABI version; no closed batch-copy entry point is named anywhere in
+    the shipped artefact (the CUDA runtime is linked shared, not static)."""
     library.mpb200_version.restype = ctypes.c_int
-    assert library.mpb200_version() >= 100
+    header = int(re.search(r"#define\s+MPB200_VERSION\s+(\d+)", open(HEADER).read()).group(1))
+    from importlib import import_module
+    assert library.mpb200_version() == header == import_module("matching_pursuit_b200._lib").ABI_VERSION
+    blob = open(mpb.LIB_PATH, "rb").read()
+    assert b"MemcpyBatchAsync" not in blob
 
 
 def test_signatures_carry_no_torch_types():

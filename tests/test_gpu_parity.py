@@ -14,7 +14,7 @@ import torch
 
 import matching_pursuit_b200 as mpb
 from oracle import mp_oracle as O
-from parity import MARGIN, RTOL, compare_trace, compare_with_oracle_trace
+from parity import MARGIN, RTOL, compare_trace, compare_with_oracle_trace, compare_with_resync, resync_against_trace
 
 pytestmark = pytest.mark.gpu
 
@@ -32,6 +32,31 @@ def run_plan(signal, d, steps, mode="recorrelate", atom_range=None):
     return atom.cpu().numpy(), pos.cpu().numpy(), val.cpu().numpy(), res.cpu().numpy()
 
 
+def plan_runner(d, n, max_batch, mode, **kw):
+    """``run(signals (b, N) numpy, steps)`` for parity.compare_with_resync: one plan, re-used for the restarts."""
+    plan = mpb.Plan(d.shape[0], d.shape[-1], n, max_batch, mode=mode, device=DEV, **kw).set_dictionary(d)
+
+    def run(signals, steps):
+        sig = torch.from_numpy(np.ascontiguousarray(signals, dtype=np.float32)).to(DEV)
+        out = plan.sparse_code(sig, steps)
+        torch.cuda.synchronize()
+        return tuple(t.cpu().numpy() for t in out)
+
+    return run, plan
+
+
+def check_against_trace(sig, d, tr, mode, min_fraction=0.0, **kw):
+    """Every step of every signal against the oracle trace (restarting from the oracle's residual after an
+    ambiguous step that was resolved differently); at least `min_fraction` of the (signal, step) pairs must have
+    been binding (margin above 1e-5 and amplitude above the round-off floor)."""
+    b, n = sig.shape[0], sig.shape[-1]
+    run, plan = plan_runner(d, n, b, mode, **kw)
+    rep = resync_against_trace(run, sig.numpy(), tr)
+    plan.close()
+    assert rep.checked == rep.eligible and rep.checked >= min_fraction * rep.total, rep
+    return rep
+
+
 # --------------------------------------------------------------------------
 # golden vectors from the live reference
 # --------------------------------------------------------------------------
@@ -41,8 +66,14 @@ def run_plan(signal, d, steps, mode="recorrelate", atom_range=None):
 def test_golden_sparse_code(path, mode):
     g = np.load(path)
     sig, d = torch.from_numpy(g["signal"]), torch.from_numpy(g["d"])
-    atom, pos, val, res = run_plan(sig, d, int(g["steps"]), mode)
-    compare_trace(g["atom"], g["pos"], g["absval"], g["margin"], g["residual"][:, 0], atom.T, pos.T, val.T, res)
+    b, n = sig.shape[0], sig.shape[-1]
+    run, plan = plan_runner(d, n, b, mode)
+    rep = compare_with_resync(run, g["signal"].reshape(b, n), O.unit_norm(d).numpy(), g["atom"], g["pos"], g["val"],
+                              g["margin"], g["residual"].reshape(b, n))
+    plan.close()
+    # every golden case but the all-zero signal and the 64-sample one holds a majority of binding steps
+    floor = 0 if ("zero" in path or "single_atom" in path) else 0.5
+    assert rep.checked == rep.eligible and rep.checked >= floor * rep.total, rep
 
 
 def test_golden_zero_signal_is_exact():
@@ -122,9 +153,8 @@ def test_oracle_parity(case, mode):
     k, a, n, b, s, family = case
     sig, d = make_case(*case)
     tr = O.greedy_pursuit(sig, d, s, want_margin=True)
-    atom, pos, val, res = run_plan(sig, d, s, mode)
-    checked = compare_with_oracle_trace(tr, atom, pos, val, res)
-    assert checked > 0
+    rep = check_against_trace(sig, d, tr, mode, min_fraction=0.9)
+    assert rep.checked > 0
 
 
 def _fuzz_shapes():
@@ -148,7 +178,7 @@ def test_random_shapes_all_schedules_against_oracle(shape):
     for mode in ("recorrelate", "full", "gram", "sgram"):
         atom, pos, val, res = run_plan(sig, d, s, mode)
         assert ((atom >= 0) & (atom < k)).all() and ((pos >= 0) & (pos < n)).all(), mode
-        compare_with_oracle_trace(tr, atom, pos, val, res)
+        check_against_trace(sig, d, tr, mode)
 
 
 @pytest.mark.parametrize("refresh", [0, 50])
@@ -160,12 +190,11 @@ def test_gram_mode_long_run_against_oracle(refresh):
     d = O.make_dictionary(k, a, seed=11)
     sig = torch.cat([O.make_planted_signals(d, 1, n, 150, seed=12), O.make_noise_signals(1, n, seed=13)], dim=0)
     tr = O.greedy_pursuit(sig, d, s, want_margin=True)
-    plan = mpb.Plan(k, a, n, b, mode="gram", device=DEV).set_dictionary(d).set_refresh_every(refresh)
+    run, plan = plan_runner(d, n, b, "gram")
+    plan.set_refresh_every(refresh)
     assert plan.mode == "gram" and plan.info.gram_bytes == k * k * 2 * a * 4
-    atom, pos, val, res = plan.sparse_code(sig.to(DEV), s)
-    checked = compare_with_oracle_trace(tr, atom.cpu().numpy(), pos.cpu().numpy(), val.cpu().numpy(),
-                                        res.cpu().numpy())
-    assert checked >= 100
+    rep = resync_against_trace(run, sig.numpy(), tr)
+    assert rep.checked == rep.eligible and rep.checked >= 0.9 * rep.total, rep
     assert int((tr.pos + a > n).sum()) > 0      # the case does contain truncated winners
 
 
@@ -176,12 +205,11 @@ def test_sgram_mode_long_run_against_oracle(refresh):
     d = O.make_dictionary(k, a, seed=11)
     sig = torch.cat([O.make_planted_signals(d, 1, n, 150, seed=12), O.make_noise_signals(1, n, seed=13)], dim=0)
     tr = O.greedy_pursuit(sig, d, s, want_margin=True)
-    plan = mpb.Plan(k, a, n, b, mode="sgram", device=DEV).set_dictionary(d).set_refresh_every(refresh)
+    run, plan = plan_runner(d, n, b, "sgram")
+    plan.set_refresh_every(refresh)
     assert plan.mode == "sgram" and plan.info.gram_bytes == 0 and plan.fft_size2 == 512
-    atom, pos, val, res = plan.sparse_code(sig.to(DEV), s)
-    checked = compare_with_oracle_trace(tr, atom.cpu().numpy(), pos.cpu().numpy(), val.cpu().numpy(),
-                                        res.cpu().numpy())
-    assert checked >= 100
+    rep = resync_against_trace(run, sig.numpy(), tr)
+    assert rep.checked == rep.eligible and rep.checked >= 0.9 * rep.total, rep
 
 
 def test_sgram_sub_batches_equal_one_batch():
@@ -223,8 +251,8 @@ def test_config1_full_size():
     d = O.make_dictionary(512, 512, seed=0)
     sig = O.make_planted_signals(d, 1, 2 ** 15, 32, seed=1)
     tr = O.greedy_pursuit(sig, d, 32, want_margin=True)
-    atom, pos, val, res = run_plan(sig, d, 32)
-    assert compare_with_oracle_trace(tr, atom, pos, val, res) >= 16
+    for mode in ("recorrelate", "sgram", "gram"):
+        check_against_trace(sig, d, tr, mode, min_fraction=0.9)
 
 
 def test_host_entry_equals_device_entry():
@@ -263,8 +291,9 @@ def test_atom_sharded_stepwise_equals_oracle():
     res = plans[0].residual().cpu().numpy()
     for p in plans[1:]:
         assert np.array_equal(p.residual().cpu().numpy(), res)
-    compare_trace(tr.atom.numpy(), tr.pos.numpy(), tr.val.abs().numpy(), tr.margin.numpy(), tr.residual.numpy()[:, 0],
-                  np.stack(atoms), np.stack(poss), np.stack(vals), res)
+    checked = compare_trace(tr.atom.numpy(), tr.pos.numpy(), tr.val.numpy(), tr.margin.numpy(), tr.residual.numpy()[:, 0],
+                            np.stack(atoms), np.stack(poss), np.stack(vals), res)
+    assert checked >= 0.9 * s * b
 
 
 @pytest.mark.parametrize("mode", ["recorrelate", "sgram"])
@@ -301,7 +330,7 @@ def test_atom_sharded_fused_exchange_equals_oracle(mode):
     for o in outs[1:]:
         for x, y in zip(outs[0], o):
             assert torch.equal(x, y)
-    assert compare_with_oracle_trace(tr, atom, pos, val, res) > 0
+    assert compare_with_oracle_trace(tr, atom, pos, val, res) >= 0.9 * s * b
 
 
 # --------------------------------------------------------------------------

@@ -33,8 +33,8 @@ def test_shards_partition_the_range(total, world):
 class _FakePlan:
     closed = 0
 
-    def __init__(self, nbytes, max_batch=8):
-        self.device_bytes, self.max_batch = nbytes, max_batch
+    def __init__(self, nbytes, max_batch=8, pins=0):
+        self.device_bytes, self.max_batch, self.pins = nbytes, max_batch, pins
 
     def close(self):
         _FakePlan.closed += 1
@@ -49,11 +49,20 @@ def test_plan_cache_evicts_oldest_first_within_budget():
             mmp._PLAN_CACHE[(0, i)] = _FakePlan(100)
         mmp._PLAN_CACHE[(1, 0)] = _FakePlan(10_000)                  # another device: not counted against device 0
         mmp._evict_until(0, max_bytes=350, max_entries=10)
-        # oldest entries go first, whatever device they sit on, until device 0 is within its budget
+        # device 0's oldest idle entries go first until it is within its budget; other devices are left alone
         assert [k for k in mmp._PLAN_CACHE if k[0] == 0] == [(0, 2), (0, 3), (0, 4)]
         assert _FakePlan.closed == 2 and (1, 0) in mmp._PLAN_CACHE
         mmp._evict_until(0, max_bytes=10 ** 9, max_entries=2)
-        assert len(mmp._PLAN_CACHE) <= 2
+        assert [k for k in mmp._PLAN_CACHE if k[0] == 0] == [(0, 3), (0, 4)] and (1, 0) in mmp._PLAN_CACHE
+        # a plan somebody holds (`with plan:`) is never closed, however far over budget the cache is
+        mmp._PLAN_CACHE[(0, 3)].pins = 1
+        mmp._evict_until(0, max_bytes=0, max_entries=0)
+        assert [k for k in mmp._PLAN_CACHE if k[0] == 0] == [(0, 3)] and (1, 0) in mmp._PLAN_CACHE
+        mmp.clear_plan_cache(0)
+        assert (0, 3) in mmp._PLAN_CACHE and (1, 0) in mmp._PLAN_CACHE
+        mmp._PLAN_CACHE[(0, 3)].pins = 0
+        mmp.clear_plan_cache()
+        assert not mmp._PLAN_CACHE
     finally:
         mmp._PLAN_CACHE.clear()
         mmp._PLAN_CACHE.update(saved)

@@ -141,3 +141,36 @@ def test_mp_forward():
     g = np.load(os.path.join(GOLDEN, "mp_forward.npz"))
     ch = O.mp_forward(torch.from_numpy(g["atoms"]), torch.from_numpy(g["audio"]), 256, 5)
     np.testing.assert_allclose(ch.numpy(), g["channels"], rtol=1e-5, atol=1e-7)
+
+
+# --------------------------------------------------------------------------
+# headline shapes: inputs regenerate from their seeds; the oracle follows the reference there too
+# --------------------------------------------------------------------------
+def _headline_prefix(name, steps):
+    """First `steps` iterations of the oracle at a headline shape against the reference's recorded trace."""
+    from headline_inputs import load_single
+    g, d, sig = load_single(name)
+    tr = O.greedy_pursuit(sig, d, steps)
+    assert np.array_equal(tr.atom.numpy(), g["atom"][:steps]) and np.array_equal(tr.pos.numpy(), g["pos"][:steps])
+    np.testing.assert_allclose(tr.val.numpy(), g["val"][:steps], rtol=1e-5)
+    return g, tr
+
+
+@pytest.mark.parametrize("name,steps", [("hl_c2_k512_a1024_n32768_b4_s64", 4), ("hl_long_k64_a4096_n32768_b2_s24", 24),
+                                        ("hl_long_k32_a8192_n32768_b2_s24", 24), ("hl_long_k16_a16384_n65536_b1_s16", 16)])
+def test_headline_inputs_and_oracle_prefix(name, steps):
+    g, tr = _headline_prefix(name, steps)
+    if steps == int(g["steps"]):
+        np.testing.assert_allclose(tr.residual.numpy().reshape(g["residual"].shape), g["residual"], rtol=1e-5, atol=1e-6)
+
+
+def test_headline_inputs_regenerate():
+    """The two large cases are not re-run on the CPU (minutes): their inputs must regenerate bit-for-bit, and the
+    recorded traces must be binding (every step above the 1e-5 margin)."""
+    from headline_inputs import HEADLINE_SINGLE, load_multiband, load_single
+    for name in HEADLINE_SINGLE:
+        g, d, sig = load_single(name)
+        assert (g["margin"] > MARGIN).mean() >= 0.9
+    g, x, dicts, bands = load_multiband()
+    for size in (int(s) for s in g["sizes"]):
+        assert (g[f"margin_{size}"] > MARGIN).mean() >= 0.9
