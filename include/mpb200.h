@@ -97,6 +97,12 @@ int mpb200_plan_info_get(mpb200_plan_t plan, mpb200_plan_info* info);
  * the only allocation the library makes after plan creation). */
 #define MPB200_OPT_MAX_STEPS 3
 #define MPB200_DEFAULT_MAX_STEPS 1024
+/* MPB200_OPT_POSITION_FREE (SGRAM mode, blocks of >= 128 positions): 1 = the block/row maxima tables carry block
+ * starts instead of exact positions and the kernel that applies a winner resolves its exact position from the
+ * resident map; 0 = exact positions everywhere.  Chosen automatically at plan creation (on when the refresh kernel
+ * dominates: >= 16384 (atom pair, signal) work items per iteration); results are identical either way.  Takes
+ * effect from the next mpb200_begin / mpb200_sparse_code. */
+#define MPB200_OPT_POSITION_FREE 4
 int mpb200_plan_set_option(mpb200_plan_t plan, int option, long long value);
 
 /* Per-kernel device timing of the pursuit loop (bench / profiling aid, no

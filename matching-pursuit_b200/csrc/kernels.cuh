@@ -1010,6 +1010,11 @@ struct DeltaArgs {
 #ifndef MPB_DELTA_NOPOS_MIN_ITEMS
 #define MPB_DELTA_NOPOS_MIN_ITEMS 16384
 #endif
+#ifndef MPB_DELTA_DEFER
+#define MPB_DELTA_DEFER 1      // three CTA barriers per item instead of four: the row maxima of an item are re-derived
+                               // one item later, in the segment where the other warps reduce block maxima (of which the
+                               // row warps then take fewer), and the map window is requested after the first barrier
+#endif
 #ifndef MPB_DELTA_SPREF
 #define MPB_DELTA_SPREF 1      // the next item's winner spectrum is bulk-copied (TMA) into the idle FFT buffer while the
                                // block/row maxima of the current item are reduced; the product phase then reads it from
@@ -1047,9 +1052,10 @@ k_delta(const DeltaArgs a) {
     C32* sm = stw2 + 256 + (size_t)sb * F::SMEM_CPX;
     float* st0 = reinterpret_cast<float*>(stw2 + 256 + (size_t)NT * F::SMEM_CPX) + (size_t)sb * 2 * a.cap;
     float* st1 = st0 + a.cap;
-    __shared__ float2 s_bv_static[NT * 64];
+    constexpr bool DEFER = MPB_DELTA_DEFER && NW == 8;   // needs dedicated row warps (M2 >= 4096)
+    __shared__ float2 s_bv_static[NT * 64 * (DEFER ? 2 : 1)];
     __shared__ __align__(8) unsigned long long s_bar[2 * NT];
-    float2* sBV = s_bv_static + sb * 64;                 // [which*32 + block] = (value, position as int bits)
+    float2* sBV = s_bv_static + sb * 64 * (DEFER ? 2 : 1);   // [which*32 + block] = (value, position as int bits); DEFER: x2 (item parity)
     unsigned long long* bar = s_bar + sb;                // map window landed
     unsigned long long* barS = s_bar + NT + sb;          // winner spectrum landed (MPB_DELTA_SPREF)
     constexpr unsigned SBYTES = (unsigned)(F::SMEM_CPX * sizeof(C32));
@@ -1087,6 +1093,36 @@ k_delta(const DeltaArgs a) {
         }
     };
     if (MPB_DELTA_SPREF && tl == 0 && n_items > 0) request_spectrum(b);
+    // DEFER: the item whose row maxima are still to be re-derived (by the row warps, one item later)
+    int pv_row = -1;                                     // map row of its atom 2q; -1: none
+    int pv_win = 0;                                      // blk0 << 6 | nvb << 1 | second
+    int par = 0;                                         // which half of sBV the current item writes
+    // Row maxima of the (row, which) pair from the refreshed block maxima in `bv` and the row's previous maximum.
+    auto row_phase = [&](int row0, int which, int rblk0, int rnvb, const float2* bv, float oldv, int oldp) {
+        const size_t rowi = (size_t)row0 + which;
+        const size_t o = rowi * a.NB;
+        float v = -INFINITY;
+        int at = INT_MAX;
+        if (lane < rnvb) {
+            const float2 c = bv[which * 32 + lane];
+            v = c.x;
+            at = __float_as_int(c.y);
+            a.bm_val[o + rblk0 + lane] = v;              // coalesced publication of the refreshed blocks
+            if constexpr (!NOPOS) a.bm_pos[o + rblk0 + lane] = at;
+        }
+        const int old_b = oldp >> a.blk_shift;
+        const bool old_ok = old_b < rblk0 || old_b >= rblk0 + rnvb;
+        if (old_ok) {
+            if (lane == 31) take_better(v, at, oldv, oldp);      // nvb <= 30: lane 31 is free
+        } else {
+            rescan_row(a.bm_val + o, NOPOS ? nullptr : a.bm_pos + o, a.NB, rblk0, rnvb, lane, v, at, a.blk_shift);
+        }
+        warp_argmax(v, at);
+        if (lane == 0) {
+            a.row_val[rowi] = v;
+            a.row_pos[rowi] = (at == INT_MAX) ? 0 : at;
+        }
+    };
     for (; n_items > 0; --n_items, b = (b + 1 == a.batch ? 0 : b + 1), g += (b == 0)) {
         const GramUpdate u = a.upd[b];
         const int b_next = (b + 1 == a.batch ? 0 : b + 1);
@@ -1106,21 +1142,30 @@ k_delta(const DeltaArgs a) {
         const int cnt = min(nvb << a.blk_shift, a.NS - start);          // staged floats per row (multiple of 4)
         float* __restrict__ m0 = a.map + ((size_t)b * a.nloc + 2 * q) * a.NS + start;
         float* __restrict__ m1 = m0 + a.NS;
-        if (tl == 0 && q_ok) {
+        auto request_window = [&]() {                    // tl == 0
             bulk_wait_read0();                           // the previous item's stores have left the staging rows
             const unsigned bytes = (unsigned)cnt * 4u;
             mbar_expect_tx(bar, second ? 2u * bytes : bytes);
             bulk_load(st0, m0, bytes, bar);
             if (second) bulk_load(st1, m1, bytes, bar);
-        }
-        // the old row maxima are fetched now so that the row phase at the end never waits on memory
+        };
+        if (!DEFER && tl == 0 && q_ok) request_window();
+        // the old row maxima are fetched now so that the row phase never waits on memory (DEFER: those of the
+        // PREVIOUS item, whose row phase runs during this one)
         float old_v[NROW];
         int old_p[NROW];
 #pragma unroll
         for (int i = 0; i < NROW; ++i) {
             const int which = which0 + i;
-            const bool mine = q_ok && which >= 0 && which < 2 && (which == 0 || second);
-            const size_t rowi = (size_t)b * a.nloc + 2 * q + (mine ? which : 0);
+            bool mine;
+            size_t rowi;
+            if constexpr (DEFER) {
+                mine = pv_row >= 0 && which >= 0 && which < 2 && (which == 0 || (pv_win & 1));
+                rowi = (size_t)(mine ? pv_row + which : 0);
+            } else {
+                mine = q_ok && which >= 0 && which < 2 && (which == 0 || second);
+                rowi = (size_t)b * a.nloc + 2 * q + (mine ? which : 0);
+            }
             old_v[i] = mine ? __ldg(a.row_val + rowi) : 0.f;
             old_p[i] = mine ? __ldg(a.row_pos + rowi) : 0;
         }
@@ -1158,6 +1203,9 @@ k_delta(const DeltaArgs a) {
         if constexpr (MPB_TWGEN && F::R1 >= 4) F::template pass1_gen<1>(r, tl, sm, a.tw1);
         else F::template pass1<1>(r, tl, sm, a.tw1);
         __syncthreads();
+        // DEFER: every warp has left the previous item's block reduction, so its staging rows may be refilled;
+        // the copy lands behind the two remaining passes
+        if (DEFER && tl == 0 && q_ok) request_window();
         F::template pass2<1>(r, tl, sm, stw2);
         __syncthreads();
         F::template pass3<1>(r, tl, sm);
@@ -1215,6 +1263,12 @@ k_delta(const DeltaArgs a) {
             bulk_commit();
         }
         if (MPB_DELTA_SPREF && tl == 0 && n_items > 1) request_spectrum(b_next);
+        if constexpr (DEFER) {
+            // the previous item's row maxima: its block maxima were staged before this item's barriers
+            if (pv_row >= 0 && which0 >= 0 && which0 < 2 && (which0 == 0 || (pv_win & 1)))
+                row_phase(pv_row, which0, pv_win >> 6, (pv_win >> 1) & 31, sBV + (par ^ 1) * 64, old_v[0], old_p[0]);
+        }
+        float2* sBVw = sBV + (DEFER ? par * 64 : 0);
         if (q_ok) {
             // (row, block) tasks are dealt round-robin to the warps; the refreshed (max, position) pairs
             // only go to shared memory here -- the row warps publish them to bm_val / bm_pos.
@@ -1222,12 +1276,16 @@ k_delta(const DeltaArgs a) {
             if (blk >= 128 && start + (nvb << a.blk_shift) <= a.N) {   // whole blocks of 128 / 256: one / two float4 per lane
                 const float* __restrict__ rowl = st0 + 4 * lane;
                 const int sh = a.blk_shift;
-                int o = warp << sh, slot = warp;                  // offset into the staging rows, slot in sBV
-                for (int task = warp; task < ntask; task += NW, o += NW << sh, slot += NW) {
-                    if (task >= nvb && task - NW < nvb) {         // crossing from row 0 to row 1
-                        o += a.cap - (nvb << sh);
-                        slot += 32 - nvb;
-                    }
+                // DEFER: the two row warps have just re-derived a row maximum each; they take the last (up to) four
+                // tasks, the other warps share the rest
+                const int nrt = DEFER ? min(ntask, 4) : 0;
+                const int t_first = !DEFER ? warp : (warp < RW0 ? warp : ntask - nrt + 2 * (warp - RW0));
+                const int t_end = !DEFER ? ntask : (warp < RW0 ? ntask - nrt : min(ntask, t_first + 2));
+                const int t_step = !DEFER ? NW : (warp < RW0 ? RW0 : 1);
+                for (int task = t_first; task < t_end; task += t_step) {
+                    const int row1 = task >= nvb ? 1 : 0;
+                    const int slot = task + row1 * (32 - nvb);    // which * 32 + block
+                    const int o = row1 * a.cap + ((task - row1 * nvb) << sh);   // offset into the staging rows
                     const float4 c0 = *reinterpret_cast<const float4*>(rowl + o);
                     float4 c1 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
                     if (blk == 256) c1 = *reinterpret_cast<const float4*>(rowl + o + 128);
@@ -1237,7 +1295,7 @@ k_delta(const DeltaArgs a) {
                     v = __int_as_float(kmax ^ ((kmax >> 31) & 0x7fffffff));
                     if (!(v == v)) v = -INFINITY;                 // a NaN in the map never wins (as in the comparison-based paths)
                     if constexpr (NOPOS) {
-                        if (lane == 0) sBV[slot] = make_float2(v, __int_as_float(start + ((slot & 31) << sh)));
+                        if (lane == 0) sBVw[slot] = make_float2(v, __int_as_float(start + ((slot & 31) << sh)));
                         continue;
                     }
                     int at = INT_MAX;                             // descending order: the lowest matching position survives
@@ -1252,8 +1310,8 @@ k_delta(const DeltaArgs a) {
                     at = __reduce_min_sync(0xffffffffu, at == INT_MAX ? at : at + 4 * lane);
                     // position = start + (block index within its row) * blk + at
                     if (lane == 0)
-                        sBV[slot] = make_float2(v, __int_as_float(at == INT_MAX ? INT_MAX
-                                                                                 : start + ((slot & 31) << sh) + at));
+                        sBVw[slot] = make_float2(v, __int_as_float(at == INT_MAX ? INT_MAX
+                                                                                  : start + ((slot & 31) << sh) + at));
                 }
             } else if (blk <= 64 && start + (nvb << a.blk_shift) <= a.N) {
                 // short atoms (blocks of 16 / 32 / 64 positions, whole blocks inside the signal): a task is 64
@@ -1285,9 +1343,9 @@ k_delta(const DeltaArgs a) {
                     const bool leader = blk == 16 ? (lane & 15) == 0 : lane == 0;
                     if (leader) {
                         const int b0 = j0 >> a.blk_shift, b1 = j1 >> a.blk_shift;   // block indices relative to blk0
-                        if (b0 < nvb) sBV[which * 32 + b0] = make_float2(v0, __int_as_float(a0 == INT_MAX ? INT_MAX : start + a0));
+                        if (b0 < nvb) sBVw[which * 32 + b0] = make_float2(v0, __int_as_float(a0 == INT_MAX ? INT_MAX : start + a0));
                         if (blk != 64 && b1 < nvb)
-                            sBV[which * 32 + b1] = make_float2(v1, __int_as_float(a1 == INT_MAX ? INT_MAX : start + a1));
+                            sBVw[which * 32 + b1] = make_float2(v1, __int_as_float(a1 == INT_MAX ? INT_MAX : start + a1));
                     }
                 }
             } else {
@@ -1305,41 +1363,33 @@ k_delta(const DeltaArgs a) {
                     }
                     warp_argmax_redux(v, at);
                     if (lane == 0)
-                        sBV[which * 32 + i] = make_float2(v, __int_as_float(at == INT_MAX ? INT_MAX : start + jbase + at));
+                        sBVw[which * 32 + i] = make_float2(v, __int_as_float(at == INT_MAX ? INT_MAX : start + jbase + at));
                 }
             }
         }
-        __syncthreads();   // block maxima staged; nobody reads the staging rows any more
+        if constexpr (DEFER) {
+            // no barrier here: this item's row maxima are re-derived during the next item (or after the loop)
+            pv_row = q_ok ? (int)((size_t)b * a.nloc + 2 * q) : -1;
+            pv_win = (blk0 << 6) | (nvb << 1) | (second ? 1 : 0);
+            par ^= 1;
+        } else {
+            __syncthreads();   // block maxima staged; nobody reads the staging rows any more
 #pragma unroll
-        for (int wi = 0; wi < NROW; ++wi) {
-            const int which = which0 + wi;
-            if (!q_ok || which < 0 || which > 1 || (which == 1 && !second)) continue;
-            const size_t rowi = (size_t)b * a.nloc + 2 * q + which;
-            const size_t o = rowi * a.NB;
-            float v = -INFINITY;
-            int at = INT_MAX;
-            if (lane < nvb) {
-                const float2 c = sBV[which * 32 + lane];
-                v = c.x;
-                at = __float_as_int(c.y);
-                a.bm_val[o + blk0 + lane] = v;           // coalesced publication of the refreshed blocks
-                if constexpr (!NOPOS) a.bm_pos[o + blk0 + lane] = at;
+            for (int wi = 0; wi < NROW; ++wi) {
+                const int which = which0 + wi;
+                if (!q_ok || which < 0 || which > 1 || (which == 1 && !second)) continue;
+                row_phase((int)((size_t)b * a.nloc + 2 * q), which, blk0, nvb, sBV, old_v[wi], old_p[wi]);
             }
-            const int old_b = old_p[wi] >> a.blk_shift;
-            const bool old_ok = old_b < blk0 || old_b >= blk0 + nvb;
-            if (old_ok) {
-                if (lane == 31) take_better(v, at, old_v[wi], old_p[wi]);   // nvb <= 30: lane 31 is free
-            } else {
-                rescan_row(a.bm_val + o, NOPOS ? nullptr : a.bm_pos + o, a.NB, blk0, nvb, lane, v, at, a.blk_shift);
-            }
-            warp_argmax(v, at);
-            if (lane == 0) {
-                a.row_val[rowi] = v;
-                a.row_pos[rowi] = (at == INT_MAX) ? 0 : at;
-            }
+            // the next item's bulk loads are issued by tl == 0 after the barrier above; warps running
+            // ahead only touch the FFT buffer until the next barrier.
         }
-        // the next item's bulk loads are issued by tl == 0 after the barrier above; warps running
-        // ahead only touch the FFT buffer until the next barrier.
+    }
+    if constexpr (DEFER) {
+        __syncthreads();       // the last item's block maxima are staged
+        if (pv_row >= 0 && which0 >= 0 && which0 < 2 && (which0 == 0 || (pv_win & 1))) {
+            const size_t rowi = (size_t)pv_row + which0;
+            row_phase(pv_row, which0, pv_win >> 6, (pv_win >> 1) & 31, sBV + (par ^ 1) * 64, a.row_val[rowi], a.row_pos[rowi]);
+        }
     }
     if (tl == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
 }

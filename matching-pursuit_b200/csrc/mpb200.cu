@@ -869,6 +869,13 @@ int mpb200_plan_set_option(mpb200_plan_t plan, int option, long long value) {
             if (value < 0) return fail(MPB200_EINVAL, "refresh_every must be >= 0");
             p->refresh_every = (int)value;
             return MPB200_OK;
+        case MPB200_OPT_POSITION_FREE:
+            if (p->mode != MPB200_MODE_SGRAM) return fail(MPB200_EINVAL, "position-free tables exist in SGRAM mode only");
+            if (value != 0 && p->blk < 128) return fail(MPB200_EINVAL, "position-free tables need blocks of >= 128 positions");
+            p->pos_free = value != 0;
+            p->delta_occ = 0;          // another kernel instantiation: re-query its occupancy
+            p->cur_batch = 0;          // tables of a batch in flight were built under the other convention
+            return MPB200_OK;
         case MPB200_OPT_FORCE_TABLES:
             p->force_tables = value != 0;
             return MPB200_OK;

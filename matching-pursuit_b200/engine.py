@@ -107,6 +107,11 @@ class Plan:
         check(self._lib.mpb200_plan_set_option(self._h, 1, int(iterations)), "mpb200_plan_set_option")
         return self
 
+    def set_position_free(self, on: bool) -> "Plan":
+        """SGRAM mode: force the position-free block tables on or off (chosen automatically otherwise)."""
+        check(self._lib.mpb200_plan_set_option(self._h, 4, int(bool(on))), "mpb200_plan_set_option")
+        return self
+
     # ---- per-kernel timing (bench aid) ----------------------------------
     def timing(self, enable: bool) -> None:
         check(self._lib.mpb200_plan_timing_enable(self._h, int(bool(enable))), "mpb200_plan_timing_enable")

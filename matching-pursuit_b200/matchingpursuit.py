@@ -289,6 +289,124 @@ def _run_held(plan: Plan, sig2d: torch.Tensor, d: torch.Tensor, n_steps: int, ap
     return plan, atom, pos, val, residual, du, work
 
 
+class _SparseCodeJob:
+    """One ``sparse_code`` call in two halves: the constructor enqueues the device work on the CURRENT stream
+    (pursuit, scaled atoms, the copy of the atom sequence the host needs for the reference's grouping) and returns
+    without waiting; :meth:`result` waits for it and builds the reference's return structures.  Callers with several
+    independent problems (the bands of a multi-band codec) start all jobs, each on its own stream, before they
+    collect any."""
+
+    def __init__(self, signal, d, n_steps, device, approx, flatten, extract_atom_embedding, visit_key_point,
+                 return_residual, local_contrast_norm, return_sparse_feature_map, compute_feature_map, mode, plan):
+        batch, channels, time = signal.shape
+        if channels != 1:
+            raise NotImplementedError("multi-channel signals fail in the reference's scatter_segments "
+                                      "(modules/matchingpursuit.py:50); only (B,1,N) is supported")
+        self.with_grad = with_grad = _needs_grad(signal, d)
+        self.batch, self.n_samples, self.n_steps = batch, time, n_steps
+        self.n_atoms, self.atom_size = n_atoms, atom_size = d.shape[0], d.shape[-1]
+        self.out_dev = signal.device
+        self.flatten, self.return_residual = flatten, return_residual
+        self.return_sparse_feature_map = return_sparse_feature_map
+        self.want_embeddings = extract_atom_embedding is not None
+        self.embeddings = embeddings = []
+        n_samples = time
+
+        dense = None
+        if (compute_feature_map is not None or extract_atom_embedding is not None or visit_key_point is not None
+                or local_contrast_norm):
+            def on_map(step, fm, du):
+                embeddings.append(extract_atom_embedding(fm, du))            # :282-283
+
+            def on_select(step, fm, k, p, v, du):
+                scaled = du[k.long()] * v[:, None] if with_grad else engine.gather_atoms(du, k, v)
+                k_host = k.tolist()
+                for j in range(batch):
+                    visit_key_point(fm[j].view(n_atoms, n_samples), k_host[j], p[j].view(1).to(torch.int64),
+                                    scaled[j].view(atom_size))
+
+            dense = dict(compute_feature_map=compute_feature_map,
+                         on_map=on_map if extract_atom_embedding is not None else None,
+                         on_select=on_select if visit_key_point is not None else None,
+                         local_contrast_norm=bool(local_contrast_norm))
+
+        if with_grad:
+            # Gradients are wanted: the greedy selection itself has none (torch.max passes gradient to the selected
+            # entry only), so the engine finds the events and PyTorch re-evaluates values, scaled atoms and residual
+            # on those fixed indices with the graph attached -- or, when a callback / LCN / a band-limited map needs
+            # the dense map under autograd, the whole loop runs as PyTorch ops ("dictionary learning stays in
+            # PyTorch", BASELINE.json; SURVEY.md 8b).
+            from . import autograd as _ag
+            work = signal.device
+            if dense is None and approx is None:
+                atom, pos, val, residual = _ag.sparse_code_differentiable(signal, d, n_steps, mode=mode, plan=plan)
+                d2 = d.reshape(n_atoms, atom_size)
+                du = d2 / (torch.norm(d2, dim=-1, keepdim=True) + 1e-8)
+            else:
+                atom, pos, val, residual, du, _ = _ag.dense_pursuit(signal, d, n_steps, approx=approx, **(dense or {}))
+        else:
+            plan_, atom, pos, val, residual, du, work = _run(signal, d, n_steps, device, approx, mode, plan, dense)
+            if du is None and not self.want_embeddings:
+                du = plan_.unit_dictionary()
+        self.work = work
+        self.residual = residual
+        if self.want_embeddings:
+            return
+        # events in the reference's order of creation: step-major, batch-minor
+        self.atom_sm = atom.t().reshape(-1)
+        self.val_sm = val.t().reshape(-1)
+        self.pos_sm = pos.t().reshape(-1)
+        self.rows = (du[self.atom_sm.long()] * self.val_sm[:, None]) if with_grad else \
+            engine.gather_atoms(du, self.atom_sm, self.val_sm)                                            # :305
+        if self.atom_sm.is_cuda:
+            self.atom_host = torch.empty(self.atom_sm.shape, dtype=self.atom_sm.dtype, pin_memory=True)
+            self.atom_host.copy_(self.atom_sm, non_blocking=True)
+            self.done = torch.cuda.Event()
+            self.done.record(torch.cuda.current_stream(self.atom_sm.device))
+        else:
+            self.atom_host, self.done = self.atom_sm, None
+
+    def result(self):
+        batch, n_samples, n_steps, out_dev, work = self.batch, self.n_samples, self.n_steps, self.out_dev, self.work
+        n_atoms, atom_size = self.n_atoms, self.atom_size
+        if getattr(self, "done", None) is not None:
+            self.done.synchronize()
+        residual = self.residual.view(batch, 1, n_samples).to(out_dev)
+        if self.want_embeddings:                                             # :332-333
+            return self.embeddings, residual
+        scatter_segments = build_scatter_segments(n_samples, atom_size, device=out_dev)
+        atom_sm, val_sm, pos_sm, rows = self.atom_sm, self.val_sm, self.pos_sm, self.rows
+        batch_sm = torch.arange(batch, device=work, dtype=torch.int64).repeat(n_steps)
+        atom_host = self.atom_host.numpy().astype(np.int64)
+        perm, seen_order = _first_seen_grouping(atom_host) if atom_host.size else (np.zeros(0, np.int64), atom_host)
+        perm_t = torch.from_numpy(perm).to(work)
+        g_atom = atom_sm.to(torch.int64)[perm_t].to(out_dev)
+        g_batch = batch_sm[perm_t].to(out_dev)
+        g_pos = pos_sm.to(torch.int64)[perm_t].to(out_dev)
+        g_rows = rows[perm_t].to(out_dev)
+        flattened = _events_from_packed(g_atom, g_batch, g_pos, g_rows)
+
+        if not self.flatten:                                                 # :335-336
+            instances = defaultdict(list)
+            counts = np.bincount(atom_host, minlength=n_atoms) if atom_host.size else np.zeros(n_atoms, np.int64)
+            start = 0
+            for ai in seen_order.tolist():
+                c = int(counts[ai])
+                group = EventList(flattened[start:start + c])
+                group.packed = (g_atom[start:start + c], g_batch[start:start + c], g_pos[start:start + c],
+                                g_rows[start:start + c])
+                instances[ai] = group
+                start += c
+            return instances, scatter_segments
+        if self.return_residual:                                             # :337-339
+            return flattened, scatter_segments, residual
+        if self.return_sparse_feature_map:                                   # :340-342, :317-318
+            sfm = torch.zeros(batch, n_atoms, n_samples, device=work)
+            sfm = sfm.index_put((batch_sm, atom_sm.to(torch.int64), pos_sm.to(torch.int64)), val_sm, accumulate=True)
+            return flattened, scatter_segments, sfm.to(out_dev)
+        return flattened, scatter_segments                                   # :343-345
+
+
 def sparse_code(signal, d, n_steps=100, device=None, approx=None, flatten=False, extract_atom_embedding=None,
                 visit_key_point=None, return_residual=False, local_contrast_norm=False,
                 return_sparse_feature_map=False, compute_feature_map=None, fft_convolution=False, *,
@@ -300,80 +418,20 @@ def sparse_code(signal, d, n_steps=100, device=None, approx=None, flatten=False,
     signal.  Return conventions follow the reference (:332-345).  ``device``
     and ``fft_convolution`` are accepted and ignored, as there.  Tensors in the
     results live on ``signal.device``."""
-    batch, channels, time = signal.shape
-    if channels != 1:
-        raise NotImplementedError("multi-channel signals fail in the reference's scatter_segments "
-                                  "(modules/matchingpursuit.py:50); only (B,1,N) is supported")
-    if _needs_grad(signal, d):
-        raise MpbError("inputs require grad: the CUDA pursuit is forward-only; run under torch.no_grad() "
-                       "or use matching_pursuit_b200.autograd.sparse_code_differentiable for the differentiable re-evaluation")
-    n_samples = time
-    n_atoms, atom_size = d.shape[0], d.shape[-1]
-    out_dev = signal.device
-    embeddings = []
+    return _SparseCodeJob(signal, d, n_steps, device, approx, flatten, extract_atom_embedding, visit_key_point,
+                          return_residual, local_contrast_norm, return_sparse_feature_map, compute_feature_map, mode,
+                          plan).result()
 
-    dense = None
-    if (compute_feature_map is not None or extract_atom_embedding is not None or visit_key_point is not None
-            or local_contrast_norm):
-        def on_map(step, fm, du):
-            embeddings.append(extract_atom_embedding(fm, du))                # :282-283
 
-        def on_select(step, fm, k, p, v, du):
-            scaled = engine.gather_atoms(du, k, v)
-            k_host = k.tolist()
-            for j in range(batch):
-                visit_key_point(fm[j].view(n_atoms, n_samples), k_host[j], p[j].view(1).to(torch.int64),
-                                scaled[j].view(atom_size))
-
-        dense = dict(compute_feature_map=compute_feature_map,
-                     on_map=on_map if extract_atom_embedding is not None else None,
-                     on_select=on_select if visit_key_point is not None else None,
-                     local_contrast_norm=bool(local_contrast_norm))
-
-    plan_, atom, pos, val, residual, du, work = _run(signal, d, n_steps, device, approx, mode, plan, dense)
-    residual = residual.view(batch, 1, n_samples).to(out_dev)
-
-    if extract_atom_embedding is not None:                                   # :332-333
-        return embeddings, residual
-
-    scatter_segments = build_scatter_segments(n_samples, atom_size, device=out_dev)
-
-    # events in the reference's order of creation: step-major, batch-minor
-    if du is None:
-        du = plan_.unit_dictionary()
-    atom_sm = atom.t().reshape(-1)
-    val_sm = val.t().reshape(-1)
-    pos_sm = pos.t().reshape(-1)
-    rows = engine.gather_atoms(du, atom_sm, val_sm)                          # :305
-    batch_sm = torch.arange(batch, device=work, dtype=torch.int64).repeat(n_steps)
-    atom_host = atom_sm.cpu().numpy().astype(np.int64)
-    perm, seen_order = _first_seen_grouping(atom_host) if atom_host.size else (np.zeros(0, np.int64), atom_host)
-    perm_t = torch.from_numpy(perm).to(work)
-    g_atom = atom_sm.to(torch.int64)[perm_t].to(out_dev)
-    g_batch = batch_sm[perm_t].to(out_dev)
-    g_pos = pos_sm.to(torch.int64)[perm_t].to(out_dev)
-    g_rows = rows[perm_t].to(out_dev)
-    flattened = _events_from_packed(g_atom, g_batch, g_pos, g_rows)
-
-    if not flatten:                                                          # :335-336
-        instances = defaultdict(list)
-        counts = np.bincount(atom_host, minlength=n_atoms) if atom_host.size else np.zeros(n_atoms, np.int64)
-        start = 0
-        for ai in seen_order.tolist():
-            c = int(counts[ai])
-            group = EventList(flattened[start:start + c])
-            group.packed = (g_atom[start:start + c], g_batch[start:start + c], g_pos[start:start + c],
-                            g_rows[start:start + c])
-            instances[ai] = group
-            start += c
-        return instances, scatter_segments
-    if return_residual:                                                      # :337-339
-        return flattened, scatter_segments, residual
-    if return_sparse_feature_map:                                            # :340-342, :317-318
-        sfm = torch.zeros(batch, n_atoms, n_samples, device=work)
-        sfm.index_put_((batch_sm, atom_sm.to(torch.int64), pos_sm.to(torch.int64)), val_sm, accumulate=True)
-        return flattened, scatter_segments, sfm.to(out_dev)
-    return flattened, scatter_segments                                       # :343-345
+def sparse_code_start(signal, d, n_steps=100, device=None, approx=None, flatten=False, extract_atom_embedding=None,
+                      visit_key_point=None, return_residual=False, local_contrast_norm=False,
+                      return_sparse_feature_map=False, compute_feature_map=None, fft_convolution=False, *,
+                      mode: str = "auto", plan: Optional[Plan] = None) -> _SparseCodeJob:
+    """:func:`sparse_code` without the wait: the device work is enqueued on the current stream and the returned
+    job's ``result()`` gives what :func:`sparse_code` returns."""
+    return _SparseCodeJob(signal, d, n_steps, device, approx, flatten, extract_atom_embedding, visit_key_point,
+                          return_residual, local_contrast_norm, return_sparse_feature_map, compute_feature_map, mode,
+                          plan)
 
 
 def sparse_code_arrays(signal, d, n_steps=100, *, approx=None, mode: str = "auto", plan: Optional[Plan] = None,
@@ -384,7 +442,9 @@ def sparse_code_arrays(signal, d, n_steps=100, *, approx=None, mode: str = "auto
     batch = signal.shape[0]
     n_samples = signal.shape[-1]
     if _needs_grad(signal, d):
-        raise MpbError("inputs require grad: the CUDA pursuit is forward-only")
+        from .autograd import sparse_code_differentiable         # indices from the engine, values re-evaluated with the graph
+        atom, pos, val, residual = sparse_code_differentiable(signal, d, n_steps, mode=mode, plan=plan)
+        return atom.to(torch.int32), pos.to(torch.int32), val, residual
     out_dev = signal.device
     _, atom, pos, val, residual, _, _ = _run(signal, d, n_steps, device, approx, mode, plan)
     return atom.to(out_dev), pos.to(out_dev), val.to(out_dev), residual.view(batch, 1, n_samples).to(out_dev)
@@ -396,12 +456,18 @@ def sparse_feature_map(signal, d, n_steps=100, device=None, approx=None, pooling
     each step adds the winning value at its (atom, position) -- the forward
     value of ``soft_dirac(f) * f`` (:100-101).  ``pooling`` is accepted and
     ignored as in the reference; ``device`` places the dense map (:84-85)."""
-    if _needs_grad(signal, d):
-        raise MpbError("inputs require grad: the CUDA pursuit is forward-only")
     b = signal.shape[0]
     sig = signal.reshape(b, 1, -1)
     n = sig.shape[-1]
     k = d.shape[0]
+    if _needs_grad(signal, d):
+        # soft_dirac's backward is the soft-max over the WHOLE flattened map (modules/sparse.py:29-43), so the
+        # gradient of this function needs the dense map of every step: the loop runs as PyTorch ops with the graph
+        # attached (callers: sparse_coding_loss :128-146; "dictionary learning stays in PyTorch")
+        from . import autograd as _ag
+        _, _, _, residual, _, fm = _ag.dense_pursuit(sig, d, n_steps, approx=approx, straight_through=True)
+        fm = fm.to(torch.device(device)) if device is not None else fm
+        return (fm, residual) if return_residual else fm
     _, atom, pos, val, residual, _, work = _run(sig, d, n_steps, device if device is not None else None, approx,
                                                 mode, plan)
     fm = torch.zeros(b, k, n, device=work)
@@ -413,6 +479,17 @@ def sparse_feature_map(signal, d, n_steps=100, device=None, approx=None, pooling
     if return_residual:
         return fm, residual.view(b, 1, n).to(signal.device)
     return fm
+
+
+def sparse_coding_loss(recon, target, d, n_steps=100, device=None, approx=None, pooling=None):
+    """modules/matchingpursuit.py:128-146: binary cross-entropy between the sparse feature maps of a reconstruction
+    (with gradient) and of its target (without), both divided by the larger of their maxima.  As in the reference
+    ``approx`` is accepted and not forwarded."""
+    r_map = sparse_feature_map(recon, d, n_steps, device=device, pooling=pooling)
+    with torch.no_grad():
+        t_map = sparse_feature_map(target, d, n_steps, device=device, pooling=pooling)
+    mx = max(r_map.max().item(), t_map.max().item())
+    return torch.nn.functional.binary_cross_entropy(r_map / mx, t_map.to(r_map.device) / mx)
 
 
 def dictionary_learning_step(signal, d, n_steps: int = 100, device=None, approx=None,

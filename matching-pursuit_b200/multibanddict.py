@@ -6,8 +6,13 @@ tensor)``, ``GlobalEventTuple = (global atom:int, batch:int, unit time,
 amplitude)``, ``BandEncodingPackage = (events, scatter, shape)``.
 
 The per-band pursuits are independent problems (they share nothing but the
-step count), so each runs on the CUDA engine through :func:`sparse_code`; the
-band split and merge run through ``mpb200_spectral_band``.  Dictionary
+step count): ``MultibandDictionaryLearning.encode`` enqueues all of them on the
+CUDA engine, one stream per band, before it waits for any; the band split and
+merge run through ``mpb200_spectral_band``.  Event lists carry the packed arrays
+they were built from (``EventList.packed`` / ``GlobalEventList.packed``), and the
+conversions between local and global tuples (:204-235, :410-443) are array
+operations on them -- per-event Python work is limited to materialising the
+reference's tuple format.  Dictionary
 learning (``learn``) keeps its atom update in PyTorch.  The STFT loss features
 of the reference module (``multiband_spectrogram*``, :19-49) are out of scope."""
 from __future__ import annotations
@@ -20,12 +25,60 @@ import torch
 
 from . import engine
 from .decompose import fft_frequency_decompose, fft_frequency_recompose, fft_resample
-from .matchingpursuit import build_scatter_segments, dictionary_learning_step, sparse_code
+from .matchingpursuit import (EventList, _events_from_packed, build_scatter_segments, dictionary_learning_step,
+                              sparse_code, sparse_code_start)
 
 Shape = Tuple
 LocalEventTuple = Tuple[int, int, int, torch.Tensor]
 GlobalEventTuple = Tuple[int, int, float, float]
 BandEncodingPackage = Tuple[List[LocalEventTuple], Callable, Shape]
+
+
+class GlobalEventList(list):
+    """A list of GlobalEventTuples that also carries them as arrays: ``packed = (global atom int64 (E,),
+    batch int64 (E,), unit time float32 (E,), amplitude float32 (E,))`` in list order."""
+    packed = None
+
+
+def _packed_local(events, atom_size: int):
+    """(atom int64 (E,), batch int64 (E,), pos int64 (E,), rows float32 (E, A)) of a local event list: the arrays
+    it carries when the engine built it, else stacked from its tuples."""
+    packed = getattr(events, "packed", None)
+    if packed is not None and len(events) == packed[0].numel():
+        atom, batch, pos, rows = packed
+        return atom, batch, pos.reshape(-1), rows
+    if len(events) == 0:
+        z = torch.zeros(0, dtype=torch.int64)
+        return z, z, z, torch.zeros(0, atom_size)
+    rows = torch.stack([ev[3].reshape(atom_size) for ev in events])
+    dev = rows.device
+    return (torch.tensor([int(ev[0]) for ev in events], dtype=torch.int64, device=dev),
+            torch.tensor([int(ev[1]) for ev in events], dtype=torch.int64, device=dev),
+            torch.tensor([int(ev[2]) for ev in events], dtype=torch.int64, device=dev), rows)
+
+
+def _packed_global(events):
+    """(global atom, batch, unit time, amplitude) arrays of a global event list."""
+    packed = getattr(events, "packed", None)
+    if packed is not None and len(events) == packed[0].numel():
+        return packed
+    if len(events) == 0:
+        z = torch.zeros(0, dtype=torch.int64)
+        return z, z, torch.zeros(0), torch.zeros(0)
+    as_t = (lambda x: x.reshape(()) if isinstance(x, torch.Tensor) else torch.tensor(float(x)))
+    time = torch.stack([as_t(ev[2]).float() for ev in events])
+    amp = torch.stack([as_t(ev[3]).float().to(time.device) for ev in events])
+    dev = time.device
+    return (torch.tensor([int(ev[0]) for ev in events], dtype=torch.int64, device=dev),
+            torch.tensor([int(ev[1]) for ev in events], dtype=torch.int64, device=dev), time, amp)
+
+
+def _unique_first(x: torch.Tensor):
+    """Distinct values of a 1-D integer tensor and the index of each one's first occurrence."""
+    uniq, inverse = torch.unique(x, return_inverse=True)
+    first = torch.full((uniq.numel(),), x.numel(), dtype=torch.int64, device=x.device)
+    first = first.scatter_reduce(0, inverse, torch.arange(x.numel(), device=x.device), reduce="amin")
+    return uniq, first
 
 
 def _unit_norm(d: torch.Tensor) -> torch.Tensor:
@@ -109,6 +162,24 @@ class BandSpec(object):
     def to_amplitude(self, scaled_atom: torch.Tensor):                       # :201-202
         return torch.norm(scaled_atom)
 
+    def to_global_arrays(self, events, offset: int):
+        """The whole event list of this band as global arrays (:204-217 for every event at once):
+        (global atom, batch, unit time, amplitude)."""
+        atom, batch, pos, rows = _packed_local(events, self.atom_size)
+        return atom + offset, batch, pos.reshape(-1) / self.size, torch.norm(rows, dim=-1)
+
+    def to_local_events(self, global_atom, batch, unit_time, amplitude, offset: int) -> EventList:
+        """Global arrays of events of THIS band back to a local event list (:219-235 for every event at once):
+        sample position = trunc(unit_time * size), scaled atom = d[local] * amplitude."""
+        local = global_atom - offset
+        pos = (unit_time * self.size).to(torch.int64)                        # int(): truncation towards zero
+        d = self.d
+        rows = d[local.to(d.device)] * amplitude.to(d.device).reshape(-1, 1)
+        a_host, b_host, p_host = local.tolist(), batch.tolist(), pos.tolist()
+        out = EventList(zip(a_host, b_host, p_host, rows.unbind(0)))
+        out.packed = (local, batch, pos, rows)
+        return out
+
     def to_global_tuple(self, event: LocalEventTuple, offset: int) -> GlobalEventTuple:   # :204-217
         atom_index, batch, sample_pos, atom = event
         return (self.to_global_atom_index(atom_index, offset), batch, self.to_unit_time(sample_pos),
@@ -119,14 +190,23 @@ class BandSpec(object):
         local_index = self.to_local_atom_index(global_index, offset)
         return (local_index, batch, self.to_sample_time(unit_time), self.get_atom(local_index, amplitude))
 
-    def encode(self, batch, steps=16, extract_embeddings=None) -> BandEncodingPackage:    # :238-263
-        encoding = sparse_code(batch, self.d, steps, device=self.device, approx=self.slce, flatten=True,
-                               extract_atom_embedding=extract_embeddings,
-                               local_contrast_norm=self.local_contrast_norm)
-        if extract_embeddings:
-            return encoding
+    def encode_start(self, batch, steps=16, extract_embeddings=None):
+        """Enqueue this band's pursuit on the current stream; ``encode_finish`` collects it."""
+        return sparse_code_start(batch, self.d, steps, device=self.device, approx=self.slce, flatten=True,
+                                 extract_atom_embedding=extract_embeddings,
+                                 local_contrast_norm=self.local_contrast_norm), batch.shape, bool(extract_embeddings)
+
+    @staticmethod
+    def encode_finish(started) -> BandEncodingPackage:
+        job, shape, embeddings = started
+        encoding = job.result()
+        if embeddings:
+            return encoding                                                  # (embeddings, residual), :250-252
         instances, scatter = encoding
-        return instances, scatter, batch.shape
+        return instances, scatter, shape
+
+    def encode(self, batch, steps=16, extract_embeddings=None) -> BandEncodingPackage:    # :238-263
+        return self.encode_finish(self.encode_start(batch, steps, extract_embeddings))
 
     def decode(self, shape, all_instances, scatter):                         # :265-266
         return scatter(shape, all_instances)
@@ -197,36 +277,70 @@ class MultibandDictionaryLearning(object):
             self.bands[size].learn(band, steps)
 
     def encode(self, batch, steps, extract_embeddings=None) -> Dict[int, BandEncodingPackage]:   # :399-404
+        """The bands are independent pursuits: each is enqueued on its own stream behind the band split, and only
+        then are the results collected (the reference's serial loop over the bands, run concurrently)."""
         bands = fft_frequency_decompose(batch, self.min_size)
-        return OrderedDict((size, band.encode(bands[size], steps, extract_embeddings))
-                           for size, band in self.bands.items())
+        if not batch.is_cuda and not torch.cuda.is_available():
+            engine._require_cuda(None)
+        dev = batch.device if batch.is_cuda else engine._require_cuda(None)
+        main = torch.cuda.current_stream(dev)
+        started = OrderedDict()
+        for i, (size, band) in enumerate(self.bands.items()):
+            side = self._stream(dev, i)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                started[size] = band.encode_start(bands[size], steps, extract_embeddings)
+        out = OrderedDict((size, BandSpec.encode_finish(job)) for size, job in started.items())
+        for i in range(len(self.bands)):
+            main.wait_stream(self._stream(dev, i))
+        return out
+
+    def _stream(self, dev, i: int):
+        key = (dev.index, i)
+        if not hasattr(self, "_streams"):
+            self._streams = {}
+        if key not in self._streams:
+            self._streams[key] = torch.cuda.Stream(device=dev)
+        return self._streams[key]
 
     def get_band_from_global_atom_index(self, index: int) -> Tuple[int, BandSpec]:    # :406-408
         band_index = index // self.n_atoms
         return band_index, list(self.bands.values())[band_index]
 
     def flattened_event_tuples(self, encoding: Dict[int, BandEncodingPackage]) -> List[GlobalEventTuple]:   # :410-422
-        output = []
-        offset = 0
-        for size, package in encoding.items():
-            events, scatter, shape = package
+        """Every band's events as ``(global atom, batch, unit time, amplitude)``, bands in encoding order with
+        offsets n_atoms apart.  One array conversion per band; as in the reference the unit time is a (1,1) tensor
+        and the amplitude a 0-d tensor."""
+        parts, offset = [], 0
+        for size, (events, _, _) in encoding.items():
             band = self.bands[size]
-            for event in events:
-                output.append(band.to_global_tuple(event, offset))
+            parts.append(band.to_global_arrays(events, offset))
             offset += band.n_atoms
-        return output
+        out = GlobalEventList()
+        if not parts:
+            return out
+        atom, batch, time, amp = (torch.cat([p[i] for p in parts]) for i in range(4))
+        out.extend(zip(atom.tolist(), batch.tolist(), time.view(-1, 1, 1).unbind(0), amp.unbind(0)))
+        out.packed = (atom, batch, time, amp)
+        return out
 
     def hierarchical_event_tuples(self, encoding: List[GlobalEventTuple],
                                   original: Dict[int, BandEncodingPackage]) -> Dict[int, BandEncodingPackage]:   # :424-443
-        hierarchical = defaultdict(list)
-        for event in encoding:
-            global_index, batch, unit_time, amplitude = event
-            index, band = self.get_band_from_global_atom_index(global_index)
-            hierarchical[band.size].append(band.to_local_tuple(event, index * self.n_atoms))
+        """Back to per-band local event lists: bands keyed in order of their first event, events of a band in list
+        order (the reference's defaultdict), each converted with its band's size and dictionary."""
+        atom, batch, time, amp = _packed_global(encoding)
         final = OrderedDict()
-        for size, events in hierarchical.items():
-            _, scatter, shape = original[size]
-            final[size] = (events, scatter, shape)
+        if atom.numel() == 0:
+            return final
+        band_of = torch.div(atom, self.n_atoms, rounding_mode="floor")                 # :406-408
+        specs = list(self.bands.values())
+        uniq, first = _unique_first(band_of)
+        for band_index in uniq[torch.argsort(first)].tolist():                         # first-seen order
+            pick = torch.nonzero(band_of == band_index).reshape(-1)                    # ascending = list order
+            band = specs[band_index]
+            events = band.to_local_events(atom[pick], batch[pick], time[pick], amp[pick], band_index * self.n_atoms)
+            _, scatter, shape = original[band.size]
+            final[band.size] = (events, scatter, shape)
         return final
 
     def decode(self, d, shapes=None):                                        # :446-458

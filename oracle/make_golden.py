@@ -161,6 +161,40 @@ def main():
         ch = m.forward(audio)
     np.savez_compressed(os.path.join(OUT, "mp_forward.npz"), atoms=m.atoms.detach().numpy(),
                         audio=audio.numpy(), channels=ch.numpy())
+    # gradients through the reference's own code (callers that train through the path): sparse_coding_loss
+    # (modules/matchingpursuit.py:128-146), sparse_code with grad (:229-345) and mp.py forward (:50-67)
+    gg = torch.Generator().manual_seed(41)
+    d = (torch.randn(10, 20, generator=gg) * 0.7).requires_grad_(True)
+    target = O.make_planted_signals(O.unit_norm(d.detach()), 2, 300, 5, seed=42)
+    recon = (target + 0.1 * torch.randn(2, 1, 300, generator=gg)).requires_grad_(True)
+    loss = ref.matchingpursuit.sparse_coding_loss(recon, target, d, n_steps=6)
+    loss.backward()
+    np.savez_compressed(os.path.join(OUT, "grad_sparse_coding_loss.npz"), d=d.detach().numpy(),
+                        target=target.numpy(), recon=recon.detach().numpy(), steps=np.int64(6),
+                        loss=np.float64(loss.item()), grad_recon=recon.grad.numpy(), grad_d=d.grad.numpy())
+
+    d = (torch.randn(12, 32, generator=gg)).requires_grad_(True)
+    sig = O.make_planted_signals(O.unit_norm(d.detach()), 2, 512, 6, seed=43).requires_grad_(True)
+    w = torch.randn(32, generator=gg)
+    flat, scatter, residual = ref.matchingpursuit.sparse_code(sig, d, n_steps=8, flatten=True, return_residual=True)
+    loss = (residual ** 2).sum() + sum((a.view(-1) * w).sum() for _, _, _, a in flat)
+    loss.backward()
+    np.savez_compressed(os.path.join(OUT, "grad_sparse_code.npz"), d=d.detach().numpy(), signal=sig.detach().numpy(),
+                        w=w.numpy(), steps=np.int64(8), loss=np.float64(loss.item()),
+                        order=np.array([(ai, j, int(p)) for ai, j, p, _ in flat]),
+                        grad_signal=sig.grad.numpy(), grad_d=d.grad.numpy())
+
+    m = ref.MatchingPursuit(n_atoms=8, atom_samples=32, n_samples=256, n_iterations=5)
+    with torch.no_grad():
+        m.atoms.copy_(torch.randn(1, 8, 32, generator=gg) * 0.3)
+    audio = O.make_noise_signals(2, 256, seed=44).requires_grad_(True)
+    w = torch.randn(2, 5, 256, generator=gg)
+    ch = m.forward(audio)
+    loss = (ch * w).sum()
+    loss.backward()
+    np.savez_compressed(os.path.join(OUT, "grad_mp_forward.npz"), atoms=m.atoms.detach().numpy(),
+                        audio=audio.detach().numpy(), w=w.numpy(), channels=ch.detach().numpy(),
+                        loss=np.float64(loss.item()), grad_atoms=m.atoms.grad.numpy(), grad_audio=audio.grad.numpy())
     print("wrote", sorted(os.listdir(OUT)))
 
 

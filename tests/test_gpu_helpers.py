@@ -172,8 +172,9 @@ def test_golden_mp_forward():
         ch = m(torch.from_numpy(g["audio"]).to(DEV))
     assert ch.shape == (2, 5, 256)
     close(ch.cpu(), g["channels"], rel=1e-4)
-    with pytest.raises(mpb.MpbError):
-        m(torch.from_numpy(g["audio"]).to(DEV))          # grad enabled: forward-only engine refuses
+    ch2 = m(torch.from_numpy(g["audio"]).to(DEV))        # grad enabled: same values, graph attached (fixed-index form)
+    assert ch2.requires_grad
+    close(ch2.detach().cpu(), g["channels"], rel=1e-4)
 
 
 def test_multiband_config4_shapes():

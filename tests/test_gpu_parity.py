@@ -212,6 +212,28 @@ def test_sgram_mode_long_run_against_oracle(refresh):
     assert rep.checked == rep.eligible and rep.checked >= 0.9 * rep.total, rep
 
 
+@pytest.mark.parametrize("case", [(64, 1024, 8192, 3, 40), (12, 2048, 16384, 2, 24), (33, 700, 5000, 2, 30)],
+                         ids=["A1024", "A2048", "A700"])
+def test_sgram_position_free_tables_equal_exact_positions(case):
+    """SGRAM's position-free block tables (on by default only for large batches) must give bit-identical events
+    and residuals to the exact-position tables, and both must follow the oracle; noise in the second signal makes
+    truncated winners (the FFT route that mixes exact positions into the tables) common."""
+    k, a, n, b, s = case
+    d = O.make_dictionary(k, a, seed=21)
+    sig = torch.cat([O.make_planted_signals(d, b - 1, n, s // 2, seed=22), O.make_noise_signals(1, n, seed=23)], dim=0)
+    tr = O.greedy_pursuit(sig, d, s, want_margin=True)
+    outs = {}
+    for on in (False, True):
+        run, plan = plan_runner(d, n, b, "sgram")
+        plan.set_position_free(on)
+        outs[on] = run(sig.numpy().reshape(b, n), s)
+        rep = resync_against_trace(run, sig.numpy(), tr)
+        assert rep.checked == rep.eligible and rep.checked >= 0.9 * rep.total, rep
+        plan.close()
+    for x, y in zip(outs[False], outs[True]):
+        assert np.array_equal(x, y)
+
+
 def test_sgram_sub_batches_equal_one_batch():
     """A resident-map budget that holds 3 of 7 signals: the batch is walked in balanced sub-batches
     and every signal gets the result it gets alone (signals are independent problems)."""
@@ -393,6 +415,7 @@ def test_dropin_callbacks_see_the_dense_map():
     def cfm(residual, du):
         calls.append(tuple(residual.shape))
         plan = mpb.get_plan(du.shape[0], du.shape[1], residual.shape[-1], residual.shape[0], residual.device)
+        plan.set_dictionary(du, normalize=False)
         return plan.correlate(residual.view(residual.shape[0], -1))
 
     flat, _ = mpb.sparse_code(sig.to(DEV), d.to(DEV), s, flatten=True, compute_feature_map=cfm)
