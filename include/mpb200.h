@@ -243,6 +243,18 @@ int mpb200_scatter_rows(float* out, int n_rows, int n_samples, const float* rows
 int mpb200_gather_atoms(float* scaled, const float* d_unit, int n_atoms, int atom_size,
                         const int32_t* atom, const float* val, int n_events, void* stream);
 
+/* Atoms longer than a plan can take (mpb200_plan_create: atom_size <= MPB200_MAX_PLAN_ATOM; the reference runs
+ * 4096, 8192 and 16384 samples in experiments/archive/e_2023_3_8/experiment.py:352-358 and
+ * e_2023_12_18/experiment.py:22-24) are correlated as n_parts consecutive parts of part_len samples: the caller
+ * makes a plan for the (n_atoms * n_parts, part_len) dictionary of parts (part p of atom k in row k*n_parts + p, the
+ * last part zero padded), runs mpb200_correlate, and this call folds the parts' maps into the long atoms' map:
+ *     fm_out[b, k, t] = sum_p sub_map[b, k*n_parts + p, t + p*part_len]      (terms beyond n_samples are zero)
+ * which equals F.conv1d of modules/matchingpursuit.py:275-277 for the long atoms.  sub_map is
+ * (batch, n_atoms * n_parts, n_samples), fm_out (batch, n_atoms, n_samples). */
+#define MPB200_MAX_PLAN_ATOM 2560
+int mpb200_fold_parts(const float* sub_map, int batch, int n_atoms, int n_parts, int part_len, int n_samples,
+                      float* fm_out, void* stream);
+
 /* y = x / (||x||_2 + eps) per row -- modules/normalization.py:4-6. */
 int mpb200_unit_norm(const float* x, float* y, int rows, int cols, float eps, void* stream);
 

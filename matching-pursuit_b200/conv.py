@@ -20,6 +20,12 @@ def _dense_map(signal: torch.Tensor, atoms: torch.Tensor) -> torch.Tensor:
     b, n = signal.shape[0], signal.shape[-1]
     out_dev = signal.device
     work = signal.device if signal.is_cuda else engine._require_cuda(None)
+    if atoms.shape[1] > engine.MAX_PLAN_ATOM:          # long atoms: correlated in parts (include/mpb200.h, mpb200_fold_parts)
+        parts, n_parts = engine.split_long_atoms(engine._dev_f32(atoms, work))
+        plan = get_plan(parts.shape[0], parts.shape[1], n, b, work, "recorrelate")
+        with plan:
+            plan.set_dictionary(parts, normalize=False)
+            return engine.correlate_long(engine._dev_f32(signal, work, (b, n)), plan, atoms.shape[0], n_parts).to(out_dev)
     plan = get_plan(atoms.shape[0], atoms.shape[1], n, b, work, "recorrelate")
     plan.set_dictionary(atoms, normalize=False)        # the helpers correlate with the atoms AS GIVEN
     return plan.correlate(engine._dev_f32(signal, work, (b, n))).to(out_dev)

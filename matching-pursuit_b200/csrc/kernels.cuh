@@ -946,6 +946,9 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
     unsigned ok;
     asm volatile(
@@ -1054,15 +1057,17 @@ k_delta(const DeltaArgs a) {
     float* st1 = st0 + a.cap;
     constexpr bool DEFER = MPB_DELTA_DEFER && NW == 8;   // needs dedicated row warps (M2 >= 4096)
     __shared__ float2 s_bv_static[NT * 64 * (DEFER ? 2 : 1)];
-    __shared__ __align__(8) unsigned long long s_bar[2 * NT];
+    __shared__ __align__(8) unsigned long long s_bar[3 * NT];
     float2* sBV = s_bv_static + sb * 64 * (DEFER ? 2 : 1);   // [which*32 + block] = (value, position as int bits); DEFER: x2 (item parity)
     unsigned long long* bar = s_bar + sb;                // map window landed
     unsigned long long* barS = s_bar + NT + sb;          // winner spectrum landed (MPB_DELTA_SPREF)
+    unsigned long long* barF = s_bar + 2 * NT + sb;      // DEFER: every warp has left the block reduction (staging rows free)
     constexpr unsigned SBYTES = (unsigned)(F::SMEM_CPX * sizeof(C32));
     for (int i = threadIdx.x; i < 256; i += TPB) stw2[i] = a.tw2[i];
     if (tl == 0) {
         mbar_init(bar, 1);
         mbar_init(barS, 1);
+        mbar_init(barF, NW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
     }
@@ -1097,6 +1102,8 @@ k_delta(const DeltaArgs a) {
     int pv_row = -1;                                     // map row of its atom 2q; -1: none
     int pv_win = 0;                                      // blk0 << 6 | nvb << 1 | second
     int par = 0;                                         // which half of sBV the current item writes
+    unsigned phaseF = 0;
+    bool phaseF_armed = false;                           // a block reduction has been run (barF has a phase to wait for)
     // Row maxima of the (row, which) pair from the refreshed block maxima in `bv` and the row's previous maximum.
     auto row_phase = [&](int row0, int which, int rblk0, int rnvb, const float2* bv, float oldv, int oldp) {
         const size_t rowi = (size_t)row0 + which;
@@ -1149,7 +1156,18 @@ k_delta(const DeltaArgs a) {
             bulk_load(st0, m0, bytes, bar);
             if (second) bulk_load(st1, m1, bytes, bar);
         };
-        if (!DEFER && tl == 0 && q_ok) request_window();
+        if constexpr (DEFER) {
+            // the staging rows are free once every warp has left the previous item's block reduction (each warp
+            // arrives on barF there): usually long ago, so the window is requested right away and lands behind all
+            // three passes
+            if (tl == 0) {
+                if (phaseF_armed) {
+                    while (!mbar_try_wait(barF, phaseF)) {}
+                    phaseF ^= 1u;
+                }
+                if (q_ok) request_window();
+            }
+        } else if (tl == 0 && q_ok) request_window();
         // the old row maxima are fetched now so that the row phase never waits on memory (DEFER: those of the
         // PREVIOUS item, whose row phase runs during this one)
         float old_v[NROW];
@@ -1203,9 +1221,6 @@ k_delta(const DeltaArgs a) {
         if constexpr (MPB_TWGEN && F::R1 >= 4) F::template pass1_gen<1>(r, tl, sm, a.tw1);
         else F::template pass1<1>(r, tl, sm, a.tw1);
         __syncthreads();
-        // DEFER: every warp has left the previous item's block reduction, so its staging rows may be refilled;
-        // the copy lands behind the two remaining passes
-        if (DEFER && tl == 0 && q_ok) request_window();
         F::template pass2<1>(r, tl, sm, stw2);
         __syncthreads();
         F::template pass3<1>(r, tl, sm);
@@ -1369,6 +1384,9 @@ k_delta(const DeltaArgs a) {
         }
         if constexpr (DEFER) {
             // no barrier here: this item's row maxima are re-derived during the next item (or after the loop)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(barF);            // this warp reads the staging rows no more
+            phaseF_armed = true;
             pv_row = q_ok ? (int)((size_t)b * a.nloc + 2 * q) : -1;
             pv_win = (blk0 << 6) | (nvb << 1) | (second ? 1 : 0);
             par ^= 1;
@@ -1560,6 +1578,24 @@ k_scatter(float* __restrict__ out, int N, const float* __restrict__ src, int n_s
 #pragma unroll
     for (int u = 0; u < 4; ++u)
         if (t[u] < N) out[(size_t)b * N + t[u]] = acc[u];
+}
+
+// Long atoms (longer than one window transform can hold) are correlated as P consecutive parts of L samples:
+//     fm[b, k, t] = sum_p sub[b, k*P + p, t + p*L],   terms with t + p*L >= N are zero (the signal ends there)
+// where sub is the dense map of the (K*P, L) dictionary of parts.  grid = (ceil(N/256), K, B).
+__global__ void __launch_bounds__(256)
+k_fold_parts(const float* __restrict__ sub, int K, int P, int L, int N, float* __restrict__ out) {
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= N) return;
+    const int k = blockIdx.y, b = blockIdx.z;
+    const float* __restrict__ base = sub + ((size_t)b * K + k) * P * (size_t)N;
+    float acc = 0.f;
+    for (int p = 0; p < P; ++p) {
+        const long long tt = (long long)t + (long long)p * L;
+        if (tt >= N) break;
+        acc = __fadd_rn(acc, base[(size_t)p * N + tt]);
+    }
+    out[((size_t)b * K + k) * N + t] = acc;
 }
 
 __global__ void k_gather_atoms(float* __restrict__ scaled, const float* __restrict__ dict, int K, int A,

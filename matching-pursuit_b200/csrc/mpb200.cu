@@ -1266,6 +1266,17 @@ int mpb200_gather_atoms(float* scaled, const float* d_unit, int n_atoms, int ato
     return MPB200_OK;
 }
 
+int mpb200_fold_parts(const float* sub_map, int batch, int n_atoms, int n_parts, int part_len, int n_samples,
+                      float* fm_out, void* stream) {
+    if (!sub_map || !fm_out || batch < 1 || n_atoms < 1 || n_parts < 1 || part_len < 1 || n_samples < 1)
+        return fail(MPB200_EINVAL, "bad argument");
+    if (n_atoms > 65535 || batch > 65535) return fail(MPB200_EINVAL, "n_atoms and batch must be <= 65535");
+    dim3 grid((n_samples + 255) / 256, n_atoms, batch);
+    k_fold_parts<<<grid, 256, 0, (cudaStream_t)stream>>>(sub_map, n_atoms, n_parts, part_len, n_samples, fm_out);
+    MPB_LAUNCH_CHECK("k_fold_parts");
+    return MPB200_OK;
+}
+
 int mpb200_unit_norm(const float* x, float* y, int rows, int cols, float eps, void* stream) {
     if (!x || !y || rows < 1 || cols < 1) return fail(MPB200_EINVAL, "bad argument");
     k_unit_norm<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, y, rows, cols, eps);

@@ -394,3 +394,41 @@ def band_limit(x: torch.Tensor, length: int, slce: slice) -> torch.Tensor:
                                       bins.step if len(bins) else 1, len(bins), _ptr(out), _stream_ptr(dev)),
               "mpb200_band_limit")
     return out
+
+
+MAX_PLAN_ATOM = 2560      # MPB200_MAX_PLAN_ATOM: longest atom one window transform of a plan can hold
+LONG_PART = 2048          # long atoms are correlated as consecutive parts of this many samples
+
+
+def split_long_atoms(atoms: torch.Tensor, part: int = LONG_PART):
+    """(K, A) -> ((K*P, part) parts, P): part p of atom k in row k*P + p, the last part zero padded."""
+    k, a = atoms.shape
+    p = -(-a // part)
+    padded = torch.zeros(k, p * part, device=atoms.device, dtype=torch.float32)
+    padded[:, :a] = atoms
+    return padded.view(k * p, part).contiguous(), p
+
+
+def fold_parts(sub_map: torch.Tensor, n_atoms: int, n_parts: int, part_len: int) -> torch.Tensor:
+    """``fm[b,k,t] = sum_p sub_map[b, k*P+p, t+p*L]`` (include/mpb200.h, mpb200_fold_parts)."""
+    b, _, n = sub_map.shape
+    dev = sub_map.device
+    out = torch.empty(b, n_atoms, n, device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        check(lib().mpb200_fold_parts(_ptr(sub_map), b, n_atoms, n_parts, part_len, n, _ptr(out), _stream_ptr(dev)),
+              "mpb200_fold_parts")
+    return out
+
+
+def correlate_long(signal2d: torch.Tensor, parts_plan: "Plan", n_atoms: int, n_parts: int,
+                   max_bytes: int = 2 << 30) -> torch.Tensor:
+    """Dense (B, K, N) correlation map of atoms longer than a plan can take: the plan holds the dictionary of their
+    parts (see :func:`split_long_atoms`); signals are walked in slices whose parts' map stays under ``max_bytes``."""
+    b, n = signal2d.shape
+    per_signal = n_atoms * n_parts * n * 4
+    step = max(1, min(b, max_bytes // max(per_signal, 1)))
+    outs = []
+    for b0 in range(0, b, step):
+        sub = parts_plan.correlate(signal2d[b0:b0 + step])
+        outs.append(fold_parts(sub, n_atoms, n_parts, parts_plan.atom_size))
+    return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)

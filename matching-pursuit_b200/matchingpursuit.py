@@ -209,8 +209,8 @@ def _needs_grad(*tensors) -> bool:
     return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
 
 
-def _pursuit_dense(sig2d: torch.Tensor, plan: Plan, n_steps: int, compute_feature_map, on_map, on_select,
-                   local_contrast_norm: bool):
+def _pursuit_dense(sig2d: torch.Tensor, plan: Optional[Plan], n_steps: int, compute_feature_map, on_map, on_select,
+                   local_contrast_norm: bool, du: Optional[torch.Tensor] = None):
     """Pursuit that materialises the dense (B,K,N) map every step -- the
     schedule of the reference loop, needed whenever a caller-supplied callback
     must see (or supply) that map (modules/matchingpursuit.py:272-273, 283,
@@ -218,7 +218,8 @@ def _pursuit_dense(sig2d: torch.Tensor, plan: Plan, n_steps: int, compute_featur
     selection and subtraction are still library kernels."""
     b, n = sig2d.shape
     dev = sig2d.device
-    du = plan.unit_dictionary()
+    du = plan.unit_dictionary() if du is None else du
+    n_atoms = du.shape[0]
     residual = sig2d.clone()
     atom = torch.empty(n_steps, b, device=dev, dtype=torch.int32)
     pos = torch.empty(n_steps, b, device=dev, dtype=torch.int32)
@@ -226,7 +227,7 @@ def _pursuit_dense(sig2d: torch.Tensor, plan: Plan, n_steps: int, compute_featur
     for step in range(n_steps):
         if compute_feature_map is not None:
             fm = compute_feature_map(residual.view(b, 1, n), du)
-            fm = fm.to(device=dev, dtype=torch.float32).contiguous().view(b, plan.n_atoms, n)
+            fm = fm.to(device=dev, dtype=torch.float32).contiguous().view(b, n_atoms, n)
         else:
             fm = plan.correlate(residual)
         if on_map is not None:
@@ -253,6 +254,8 @@ def _run(signal: torch.Tensor, d: torch.Tensor, n_steps: int, device, approx, mo
         raise NotImplementedError(
             "approx=int<N (top-k spectral bins, modules/conv.py:30-47) is defective in the reference (only atom 0 "
             "is populated) and is not part of the engine; pass approx=None, a slice, or approx>=n_samples")
+    if plan is None and a > engine.MAX_PLAN_ATOM:
+        return _run_long_atoms(sig2d, d, n_steps, approx, dense_kwargs, work)
     if plan is None:
         # the dense schedule (per-step callbacks, LCN, band-limited maps) only ever calls correlate(): a
         # re-correlation plan holds no resident map or Gram table that would go unused
@@ -261,6 +264,29 @@ def _run(signal: torch.Tensor, d: torch.Tensor, n_steps: int, device, approx, mo
         plan.set_dictionary(d)
     with plan:                       # held: further get_plan calls (below, or inside callbacks) must not evict it
         return _run_held(plan, sig2d, d, n_steps, approx, dense_kwargs, work)
+
+
+def _run_long_atoms(sig2d: torch.Tensor, d: torch.Tensor, n_steps: int, approx, dense_kwargs, work):
+    """Atoms longer than a plan's window transform (the reference runs 4096 ... 16384 samples,
+    experiments/archive/e_2023_3_8/experiment.py:352-358, e_2023_12_18/experiment.py:22-24): the dense-map schedule
+    with the correlation assembled from the atoms' 2048-sample parts (``mpb200_correlate`` on the dictionary of
+    parts + ``mpb200_fold_parts``); selection and subtraction are the usual kernels."""
+    b, n = sig2d.shape
+    k, a = d.shape[0], d.shape[-1]
+    if isinstance(approx, slice):
+        raise NotImplementedError("approx=slice with atoms longer than %d samples" % engine.MAX_PLAN_ATOM)
+    du = engine.unit_norm(engine._dev_f32(d, work).reshape(k, a))
+    parts, n_parts = engine.split_long_atoms(du)
+    plan_parts = get_plan(k * n_parts, parts.shape[1], n, b, work, "recorrelate")
+    with plan_parts:
+        plan_parts.set_dictionary(parts, normalize=False)
+        kw = dict(dense_kwargs) if dense_kwargs is not None else dict(
+            compute_feature_map=None, on_map=None, on_select=None, local_contrast_norm=False)
+        if kw["compute_feature_map"] is None:
+            kw["compute_feature_map"] = \
+                lambda residual, du_: engine.correlate_long(residual.view(b, n), plan_parts, k, n_parts)
+        atom, pos, val, residual, du = _pursuit_dense(sig2d, None, n_steps, du=du, **kw)
+    return None, atom, pos, val, residual, du, work
 
 
 def _run_held(plan: Plan, sig2d: torch.Tensor, d: torch.Tensor, n_steps: int, approx, dense_kwargs, work):

@@ -280,8 +280,6 @@ class MultibandDictionaryLearning(object):
         """The bands are independent pursuits: each is enqueued on its own stream behind the band split, and only
         then are the results collected (the reference's serial loop over the bands, run concurrently)."""
         bands = fft_frequency_decompose(batch, self.min_size)
-        if not batch.is_cuda and not torch.cuda.is_available():
-            engine._require_cuda(None)
         dev = batch.device if batch.is_cuda else engine._require_cuda(None)
         main = torch.cuda.current_stream(dev)
         started = OrderedDict()

@@ -17,7 +17,7 @@ import pytest
 import torch
 
 import matching_pursuit_b200 as mpb
-from headline_inputs import GOLDEN, HEADLINE_SINGLE, load_multiband, load_single
+from headline_inputs import GOLDEN, HEADLINE_LONG, HEADLINE_SINGLE, load_multiband, load_single
 from oracle import mp_oracle as O
 from parity import compare_with_resync
 
@@ -71,3 +71,28 @@ def test_multiband_shapes_against_reference(mode):
     for size in (int(s) for s in g["sizes"]):
         np.testing.assert_allclose(split[size].cpu().numpy(), bands[size].numpy(), rtol=1e-4, atol=2e-6)
         check(bands[size], dicts[size], g, mode, suffix=f"_{size}")
+
+
+@pytest.mark.parametrize("name", HEADLINE_LONG)
+def test_long_atoms_against_reference(name):
+    """Atoms of 4096, 8192 and 16384 samples (experiments/archive/e_2023_3_8/experiment.py:352-358,
+    e_2023_12_18/experiment.py:22-24): longer than a plan's window transform, coded through the drop-in entry
+    point, which correlates them in 2048-sample parts."""
+    g, d, sig = load_single(name)
+    b, n = sig.shape[0], sig.shape[-1]
+
+    def run(signals, steps):
+        x = torch.from_numpy(np.ascontiguousarray(signals, dtype=np.float32)).to(DEV).view(signals.shape[0], 1, n)
+        atom, pos, val, res = mpb.sparse_code_arrays(x, d.to(DEV), steps)
+        return atom.cpu().numpy(), pos.cpu().numpy(), val.cpu().numpy(), res.cpu().numpy().reshape(-1, n)
+
+    rep = compare_with_resync(run, sig.numpy().reshape(b, n), O.unit_norm(d).numpy(), g["atom"], g["pos"], g["val"],
+                              g["margin"], g["residual"])
+    assert rep.checked == rep.eligible and rep.checked >= 0.9 * rep.total, rep
+    # the reference-format entry point and the dense helper take long atoms too
+    flat, scatter, residual = mpb.sparse_code(sig.to(DEV), d.to(DEV), 4, flatten=True, return_residual=True)
+    recon = scatter(tuple(sig.shape), flat)
+    np.testing.assert_allclose((recon + residual).cpu().numpy(), sig.numpy(), atol=2e-5)
+    fm = mpb.conv.torch_conv(sig[:1].to(DEV), O.unit_norm(d).to(DEV))
+    want = O.correlate_direct(sig[:1], O.unit_norm(d))
+    np.testing.assert_allclose(fm.cpu().numpy(), want.numpy(), rtol=1e-4, atol=2e-5 * float(want.abs().max()))
