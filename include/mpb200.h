@@ -255,6 +255,16 @@ int mpb200_gather_atoms(float* scaled, const float* d_unit, int n_atoms, int ato
 int mpb200_fold_parts(const float* sub_map, int batch, int n_atoms, int n_parts, int part_len, int n_samples,
                       float* fm_out, void* stream);
 
+/* The same dense map as mpb200_correlate, computed on the TENSOR CORES instead of by FFT (BASELINE.json north_star
+ * (1)): a Toeplitz/Hankel GEMM with tcgen05.mma (kind::tf32, accumulators in tensor memory) and split-precision
+ * 3xTF32 so that fp32 argmax parity holds; the Hankel operand is expanded in shared memory.  The atoms are used as
+ * given (d is (n_atoms, atom_size), not normalised); fm_out is (batch, n_atoms, n_samples).  The plans never choose
+ * this route on their own -- it is exported so that the two routes can be measured against each other with the
+ * tensor-pipe and HBM counters (profiles/r2_gemm_vs_fft.md).  spin_blocks > 0 turns the call into a tensor-pipe
+ * peak probe: nothing is written, and every CTA issues that many extra 128x256x32 3xTF32 MMA blocks. */
+int mpb200_correlate_gemm(const float* signal, int batch, int n_samples, const float* d, int n_atoms, int atom_size,
+                          float* fm_out, int spin_blocks, void* stream);
+
 /* y = x / (||x||_2 + eps) per row -- modules/normalization.py:4-6. */
 int mpb200_unit_norm(const float* x, float* y, int rows, int cols, float eps, void* stream);
 

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 # MPB200_LIBRARY points the binding at an alternative build of the same sources (A/B timing of kernel variants)
 LIB_PATH = os.environ.get("MPB200_LIBRARY") or os.path.join(HERE, "libmpb200.so")
-SOURCES = ["mpb200.cu", "fftconv.cu"]
+SOURCES = ["mpb200.cu", "fftconv.cu", "gemm_corr.cu"]
 HEADERS = ["kernels.cuh", "fft_core.cuh", "bigfft.cuh", "types.h", "plan.h"]
 
 ABI_VERSION = 120    # MPB200_VERSION of include/mpb200.h this binding was written against
@@ -95,6 +95,7 @@ _SIGNATURES = {
     "mpb200_gather_atoms": (_i, [_p, _p, _i, _i, _p, _p, _i, _p]),
     "mpb200_unit_norm": (_i, [_p, _p, _i, _i, C.c_float, _p]),
     "mpb200_fold_parts": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
+    "mpb200_correlate_gemm": (_i, [_p, _i, _i, _p, _i, _i, _p, _i, _p]),
     "mpb200_fft_convolve": (_i, [_p, _p, _p, _i, _i, _i, _i, C.c_float, _p, _p]),
     "mpb200_exchange_create": (_i, [_p, _i, _i, _p]),
     "mpb200_exchange_connect": (_i, [_p, _p]),

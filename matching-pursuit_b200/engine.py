@@ -432,3 +432,18 @@ def correlate_long(signal2d: torch.Tensor, parts_plan: "Plan", n_atoms: int, n_p
         sub = parts_plan.correlate(signal2d[b0:b0 + step])
         outs.append(fold_parts(sub, n_atoms, n_parts, parts_plan.atom_size))
     return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+
+
+def correlate_gemm(signal2d: torch.Tensor, atoms: torch.Tensor, spin_blocks: int = 0) -> Optional[torch.Tensor]:
+    """The dense (B, K, N) correlation map of ``atoms`` (K, A), used as given, with ``signal2d`` (B, N) on the
+    tensor cores: 3xTF32 Toeplitz GEMM (include/mpb200.h, mpb200_correlate_gemm).  ``spin_blocks`` > 0: tensor-pipe
+    peak probe, returns None."""
+    dev = _require_cuda(signal2d.device)
+    sig = _dev_f32(signal2d, dev)
+    d = _dev_f32(atoms, dev)
+    b, n = sig.shape
+    out = None if spin_blocks > 0 else torch.empty(b, d.shape[0], n, device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        check(lib().mpb200_correlate_gemm(_ptr(sig), b, n, _ptr(d), d.shape[0], d.shape[1], _ptr(out), int(spin_blocks),
+                                          _stream_ptr(dev)), "mpb200_correlate_gemm")
+    return out
