@@ -243,6 +243,21 @@ int mpb200_scatter_rows(float* out, int n_rows, int n_samples, const float* rows
 int mpb200_gather_atoms(float* scaled, const float* d_unit, int n_atoms, int atom_size,
                         const int32_t* atom, const float* val, int n_events, void* stream);
 
+/* Dictionary-learning atom update -- the loop of modules/matchingpursuit.py:391-417 as one launch.  The events of a
+ * coding pass (mpb200_sparse_code + mpb200_gather_atoms) are given GROUPED BY ATOM in the reference's first-seen
+ * order: group g holds events [group_offsets[g], group_offsets[g+1]) of atom group_atom[g], inside a group in
+ * step-major, batch-minor order (:261, :321).  For every group, in order: the group's scaled atoms ev_rows[e]
+ * (atom_size samples each) are added back to `running` at (ev_batch[e], ev_pos[e]), the new atom is the unit-normed
+ * (modules/normalization.py:4-6) sum of the running-signal segments under the group's events (zero beyond the
+ * signal), it replaces row group_atom[g] of d_unit, and new_atom * ||ev_rows[e]|| is subtracted at every event.
+ *   running  (batch, n_samples) in/out: starts as a copy of the SIGNAL (:367 -- not the coding residual)
+ *   d_unit   (n_atoms, atom_size) in/out: the unit-normed dictionary the events were coded with
+ * The caller applies the final unit_norm of :417 (mpb200_unit_norm). */
+int mpb200_dictionary_update(float* running, int batch, int n_samples, float* d_unit, int n_atoms, int atom_size,
+                             const int32_t* group_offsets, const int32_t* group_atom, int n_groups,
+                             const int32_t* ev_batch, const int32_t* ev_pos, const float* ev_rows, int n_events,
+                             void* stream);
+
 /* Atoms longer than a plan can take (mpb200_plan_create: atom_size <= MPB200_MAX_PLAN_ATOM; the reference runs
  * 4096, 8192 and 16384 samples in experiments/archive/e_2023_3_8/experiment.py:352-358 and
  * e_2023_12_18/experiment.py:22-24) are correlated as n_parts consecutive parts of part_len samples: the caller

@@ -96,6 +96,7 @@ _SIGNATURES = {
     "mpb200_unit_norm": (_i, [_p, _p, _i, _i, C.c_float, _p]),
     "mpb200_fold_parts": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "mpb200_correlate_gemm": (_i, [_p, _i, _i, _p, _i, _i, _p, _i, _p]),
+    "mpb200_dictionary_update": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _i, _p, _p, _p, _i, _p]),
     "mpb200_fft_convolve": (_i, [_p, _p, _p, _i, _i, _i, _i, C.c_float, _p, _p]),
     "mpb200_exchange_create": (_i, [_p, _i, _i, _p]),
     "mpb200_exchange_connect": (_i, [_p, _p]),

@@ -1598,6 +1598,74 @@ k_fold_parts(const float* __restrict__ sub, int K, int P, int L, int N, float* _
     out[((size_t)b * K + k) * N + t] = acc;
 }
 
+// ---------------------------------------------------------------------------
+// Dictionary-learning atom update (modules/matchingpursuit.py:391-417) as ONE launch.  The events of a coding
+// pass are grouped by atom in first-seen order; the groups depend on each other through the running signal, so a
+// single CTA walks them in order and, per group:
+//   1. adds the group's scaled atoms back to the running signal            (:395-396)
+//   2. sums the segments under the group's events into the new atom        (:398-400; zero beyond the signal)
+//   3. unit-norms it: x / (||x|| + 1e-8), and stores it as row `atom`      (:402-406)
+//   4. subtracts new_atom * ||scaled atom|| at every event                  (:408-415)
+// Events of one group may overlap in time, so steps 1 and 4 go event by event with a CTA barrier in between
+// (the reference's list order); the sums of step 2 run in event order per sample.
+// Dynamic shared memory: A floats (the new atom).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_dictionary_update(float* __restrict__ running, int N, float* __restrict__ dict, int A,
+                    const int* __restrict__ group_offsets, const int* __restrict__ group_atom, int n_groups,
+                    const int* __restrict__ ev_batch, const int* __restrict__ ev_pos, const float* __restrict__ ev_rows) {
+    extern __shared__ float s_atom[];
+    __shared__ double s_part[32];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    auto block_sum = [&](double v) -> double {          // every thread returns the CTA-wide sum
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        __syncthreads();
+        if ((tid & 31) == 0) s_part[tid >> 5] = v;
+        __syncthreads();
+        double t = 0.0;
+        for (int w = 0; w < (nthr >> 5); ++w) t += s_part[w];
+        return t;
+    };
+    for (int g = 0; g < n_groups; ++g) {
+        const int e0 = group_offsets[g], e1 = group_offsets[g + 1];
+        for (int e = e0; e < e1; ++e) {                  // 1. add the instances back
+            float* __restrict__ r = running + (size_t)ev_batch[e] * N + ev_pos[e];
+            const float* __restrict__ row = ev_rows + (size_t)e * A;
+            const int keep = min(A, N - ev_pos[e]);
+            for (int i = tid; i < keep; i += nthr) r[i] = __fadd_rn(r[i], row[i]);
+            __syncthreads();
+        }
+        double sq = 0.0;                                 // 2. sum of the segments
+        for (int i = tid; i < A; i += nthr) {
+            float acc = 0.f;
+            for (int e = e0; e < e1; ++e) {
+                const int p = ev_pos[e];
+                if (p + i < N) acc = __fadd_rn(acc, running[(size_t)ev_batch[e] * N + p + i]);
+            }
+            s_atom[i] = acc;
+            sq += (double)acc * (double)acc;
+        }
+        const float denom = __fadd_rn((float)sqrt(block_sum(sq)), 1e-8f);       // 3. unit norm
+        for (int i = tid; i < A; i += nthr) {
+            const float v = __fdiv_rn(s_atom[i], denom);
+            s_atom[i] = v;
+            dict[(size_t)group_atom[g] * A + i] = v;
+        }
+        __syncthreads();
+        for (int e = e0; e < e1; ++e) {                  // 4. subtract the re-scaled new atom
+            const float* __restrict__ row = ev_rows + (size_t)e * A;
+            double a2 = 0.0;
+            for (int i = tid; i < A; i += nthr) a2 += (double)row[i] * (double)row[i];
+            const float amp = (float)sqrt(block_sum(a2));
+            float* __restrict__ r = running + (size_t)ev_batch[e] * N + ev_pos[e];
+            const int keep = min(A, N - ev_pos[e]);
+            for (int i = tid; i < keep; i += nthr) r[i] = __fsub_rn(r[i], __fmul_rn(s_atom[i], amp));
+            __syncthreads();
+        }
+    }
+}
+
 __global__ void k_gather_atoms(float* __restrict__ scaled, const float* __restrict__ dict, int K, int A,
                                const int* __restrict__ atom, const float* __restrict__ val, int n_events) {
     const int e = blockIdx.x;

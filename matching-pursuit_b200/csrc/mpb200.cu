@@ -1266,6 +1266,23 @@ int mpb200_gather_atoms(float* scaled, const float* d_unit, int n_atoms, int ato
     return MPB200_OK;
 }
 
+int mpb200_dictionary_update(float* running, int batch, int n_samples, float* d_unit, int n_atoms, int atom_size,
+                             const int32_t* group_offsets, const int32_t* group_atom, int n_groups,
+                             const int32_t* ev_batch, const int32_t* ev_pos, const float* ev_rows, int n_events,
+                             void* stream) {
+    if (!running || !d_unit || batch < 1 || n_samples < 1 || n_atoms < 1 || atom_size < 1 || n_groups < 0 || n_events < 0)
+        return fail(MPB200_EINVAL, "bad argument");
+    if (n_groups == 0 || n_events == 0) return MPB200_OK;
+    if (!group_offsets || !group_atom || !ev_batch || !ev_pos || !ev_rows) return fail(MPB200_EINVAL, "null event array");
+    const size_t smem = (size_t)atom_size * sizeof(float);
+    if (smem > 200 * 1024) return fail(MPB200_EINVAL, "atom too long for the update kernel's shared-memory copy");
+    MPB_CUDA(allow_smem(k_dictionary_update, smem));
+    k_dictionary_update<<<1, 1024, smem, (cudaStream_t)stream>>>(running, n_samples, d_unit, atom_size, group_offsets,
+                                                                 group_atom, n_groups, ev_batch, ev_pos, ev_rows);
+    MPB_LAUNCH_CHECK("k_dictionary_update");
+    return MPB200_OK;
+}
+
 int mpb200_fold_parts(const float* sub_map, int batch, int n_atoms, int n_parts, int part_len, int n_samples,
                       float* fm_out, void* stream) {
     if (!sub_map || !fm_out || batch < 1 || n_atoms < 1 || n_parts < 1 || part_len < 1 || n_samples < 1)

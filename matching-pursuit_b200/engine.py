@@ -447,3 +447,18 @@ def correlate_gemm(signal2d: torch.Tensor, atoms: torch.Tensor, spin_blocks: int
         check(lib().mpb200_correlate_gemm(_ptr(sig), b, n, _ptr(d), d.shape[0], d.shape[1], _ptr(out), int(spin_blocks),
                                           _stream_ptr(dev)), "mpb200_correlate_gemm")
     return out
+
+
+def dictionary_update(running: torch.Tensor, d_unit: torch.Tensor, group_offsets: torch.Tensor, group_atom: torch.Tensor,
+                      ev_batch: torch.Tensor, ev_pos: torch.Tensor, ev_rows: torch.Tensor) -> None:
+    """In place: the atom-update loop of modules/matchingpursuit.py:391-417 over events grouped by atom in first-seen
+    order (include/mpb200.h, mpb200_dictionary_update).  ``running`` (B, N) and ``d_unit`` (K, A) are updated."""
+    dev = running.device
+    i32 = lambda t: t.reshape(-1).to(device=dev, dtype=torch.int32).contiguous()
+    go, ga, eb, ep = i32(group_offsets), i32(group_atom), i32(ev_batch), i32(ev_pos)
+    rows = ev_rows.to(device=dev, dtype=torch.float32).contiguous()
+    with torch.cuda.device(dev):
+        check(lib().mpb200_dictionary_update(_ptr(running), running.shape[0], running.shape[-1], _ptr(d_unit),
+                                             d_unit.shape[0], d_unit.shape[1], _ptr(go), _ptr(ga), ga.numel(), _ptr(eb),
+                                             _ptr(ep), _ptr(rows), eb.numel(), _stream_ptr(dev)),
+              "mpb200_dictionary_update")

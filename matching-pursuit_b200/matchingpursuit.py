@@ -521,32 +521,24 @@ def sparse_coding_loss(recon, target, d, n_steps=100, device=None, approx=None, 
 def dictionary_learning_step(signal, d, n_steps: int = 100, device=None, approx=None,
                              local_constrast_norm: bool = False, compute_feature_map=None, fft_convolution=False, *,
                              mode: str = "auto"):
-    """One dictionary update (modules/matchingpursuit.py:348-419).  The coding
-    pass is the CUDA pursuit; the atom update stays in PyTorch: for every used
-    atom, in first-seen order, its instances are added back to a running copy
-    of the SIGNAL (:367), the atom becomes the unit-normed sum of the segments
-    under them (:400-406) and the re-scaled new atom is subtracted (:408-415)."""
+    """One dictionary update (modules/matchingpursuit.py:348-419).  The coding pass is the CUDA pursuit; the atom
+    update (:391-417) is one kernel launch (``mpb200_dictionary_update``): for every used atom, in first-seen order,
+    its instances are added back to a running copy of the SIGNAL (:367 -- not the coding residual), the atom
+    becomes the unit-normed sum of the segments under them (:400-406) and the re-scaled new atom is subtracted
+    (:408-415)."""
     batch, channels, n_samples = signal.shape
-    atom_size = d.shape[-1]
     work = _work_device(signal, device)
     with torch.no_grad():
-        d_new = engine.unit_norm(engine._dev_f32(d, work).reshape(d.shape[0], -1)).view(d.shape).clone()
-        running = engine._dev_f32(signal, work).clone()
-        instances, _ = sparse_code(signal, d, n_steps=n_steps, device=device, approx=approx,
-                                   local_contrast_norm=local_constrast_norm,
-                                   compute_feature_map=compute_feature_map, fft_convolution=fft_convolution, mode=mode)
-        flat_rows = running.view(batch * channels, n_samples)
-        for index, inst in instances.items():
-            _, bidx, pos, rows = inst.packed
-            bidx, pos, rows = bidx.to(work), pos.to(work), rows.to(work)
-            engine.scatter_rows(flat_rows, rows, bidx, pos)                   # add the instances back (:395-396)
-            padded = torch.nn.functional.pad(running.view(batch, n_samples), (0, atom_size))
-            gather_idx = pos.view(-1, 1) + torch.arange(atom_size, device=work).view(1, -1)
-            segments = padded[bidx.view(-1, 1), gather_idx]                   # (E, A)  (:369-378)
-            summed = torch.sum(segments, dim=0)                               # :398
-            new_atom = summed / (torch.norm(summed) + 1e-8)                   # unit_norm (:403-404)
-            d_new.view(d.shape[0], -1)[index] = new_atom
-            amps = torch.norm(rows, dim=-1, keepdim=True)                     # :409-411
-            engine.scatter_rows(flat_rows, -(new_atom.view(1, -1) * amps), bidx, pos)
-        out = engine.unit_norm(d_new.reshape(d.shape[0], -1)).view(d.shape)   # :417
+        d_new = engine.unit_norm(engine._dev_f32(d, work).reshape(d.shape[0], -1)).clone()
+        running = engine._dev_f32(signal, work).clone().view(batch * channels, n_samples)
+        flat, _ = sparse_code(signal, d, n_steps=n_steps, device=device, approx=approx, flatten=True,
+                              local_contrast_norm=local_constrast_norm,
+                              compute_feature_map=compute_feature_map, fft_convolution=fft_convolution, mode=mode)
+        if len(flat):
+            # the flattened list IS the grouped order: atoms in first-seen order, each atom's events together
+            atom, bidx, pos, rows = (t.to(work) for t in flat.packed)
+            starts = torch.nonzero(torch.cat([torch.ones(1, dtype=torch.bool, device=work), atom[1:] != atom[:-1]])).view(-1)
+            offsets = torch.cat([starts, torch.tensor([atom.numel()], device=work)])
+            engine.dictionary_update(running, d_new, offsets, atom[starts], bidx, pos, rows)
+        out = engine.unit_norm(d_new).view(d.shape)                           # :417
     return out.to(d.device)
