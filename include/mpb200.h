@@ -103,6 +103,12 @@ int mpb200_plan_info_get(mpb200_plan_t plan, mpb200_plan_info* info);
  * dominates: >= 16384 (atom pair, signal) work items per iteration); results are identical either way.  Takes
  * effect from the next mpb200_begin / mpb200_sparse_code. */
 #define MPB200_OPT_POSITION_FREE 4
+/* MPB200_OPT_LOCAL_CONTRAST_NORM (GRAM / SGRAM mode, un-sharded plans): 1 = the selection of mpb200_sparse_code runs
+ * on fm - avg_pool2d(fm, 9x9, stride 1, zero padding 4) over the (atom, time) plane and the reported value is the
+ * raw map value at the winner (modules/matchingpursuit.py:286-296), INCREMENTALLY: after every step only the
+ * normalised values in the winner's +-A window (+-4 columns) are recomputed from the resident map and a second
+ * block/row-max hierarchy is refreshed.  Allocates that hierarchy on first use. */
+#define MPB200_OPT_LOCAL_CONTRAST_NORM 5
 int mpb200_plan_set_option(mpb200_plan_t plan, int option, long long value);
 
 /* Per-kernel device timing of the pursuit loop (bench / profiling aid, no

@@ -630,6 +630,8 @@ struct ApplyArgs {
     int* xerr;                    // set when a record did not arrive in time
     const float* map;             // position-free tables (SGRAM): resident map (B, nloc, NS) the winner's exact position
     int NS;                       // is resolved from; null otherwise
+    const float* raw_map;         // LCN selection: row_val/row_pos are the NORMALISED tables; the event's value is the
+                                  // raw map entry at the winner (modules/matchingpursuit.py:296)
 };
 
 __device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
@@ -708,6 +710,10 @@ k_apply(const ApplyArgs a) {
     if constexpr (SELECT) {
         w = block_best(a.row_val, a.row_pos, b, a.nloc, a.atom_lo, &s_best);
         if (a.map) w = resolve_position(a.map + ((size_t)b * a.nloc + (w.atom - a.atom_lo)) * a.NS, a.N, a.blk_shift, w);
+        if (a.raw_map) {
+            const int kk = min(max(w.atom - a.atom_lo, 0), a.nloc - 1), pp = min(max(w.position, 0), a.N - 1);
+            w.value = a.raw_map[((size_t)b * a.nloc + kk) * a.NS + pp];
+        }
         if (a.world > 1) {
             __shared__ Best s_slot[64];
             w = exchange_best(a, b, w, s_slot);
@@ -1596,6 +1602,88 @@ k_fold_parts(const float* __restrict__ sub, int K, int P, int L, int N, float* _
         acc = __fadd_rn(acc, base[(size_t)p * N + tt]);
     }
     out[((size_t)b * K + k) * N + t] = acc;
+}
+
+// ---------------------------------------------------------------------------
+// Incremental local-contrast-norm selection (modules/matchingpursuit.py:286-296).  The selection runs on
+//     norm[k, t] = fm[k, t] - avg_pool2d(fm, 9x9, stride 1, zero padding 4)[k, t]
+// over the (atom, time) plane.  A step changes the raw map in the +-A window of its winner only (all rows), so the
+// normalised map changes in that window widened by 4 columns: this kernel recomputes the normalised values of the
+// whole blocks that cover it -- every row, from the RESIDENT raw map -- and refreshes a second block-max / row-max
+// hierarchy (nbm_*, nrow_*) that the selection reads.  `full` (first pass): every block of every row.
+// The 81-term sums run in the reference's order (rows outer, columns inner, one fp32 running sum, then / 81).
+// grid = (ceil(nloc / 8), batch), 256 threads: warp w owns row k0 + w; the CTA walks the window block by block with
+// a (16 rows x (blk + 8) columns) shared tile.  The row maximum is re-derived from the row's block table.
+// ---------------------------------------------------------------------------
+struct LcnArgs {
+    const float* map;        // (B, nloc, NS) raw correlation map
+    const GramUpdate* upd;   // (B) winner of the step (its +-A window is what changed); unused when full
+    float* nbm_val;          // (B, nloc, NB) block maxima of the normalised map
+    int* nbm_pos;
+    float* nrow_val;         // (B, nloc)
+    int* nrow_pos;
+    int nloc, N, NS, NB, blk_shift, A, full;
+};
+
+__global__ void __launch_bounds__(256)
+k_lcn_refresh(const LcnArgs a) {
+    extern __shared__ float s_tile[];                    // [16][blk + 8]
+    const int b = blockIdx.y, k0 = blockIdx.x * 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int blk = 1 << a.blk_shift, pitch = blk + 8;
+    int blk_lo = 0, blk_hi = a.NB;                       // blocks [blk_lo, blk_hi) are refreshed
+    if (!a.full) {
+        const int p = a.upd[b].position;
+        const int c_lo = max(0, p - a.A + 1 - 4), c_hi = min(a.N - 1, p + a.A - 1 + 4);
+        blk_lo = c_lo >> a.blk_shift;
+        blk_hi = (c_hi >> a.blk_shift) + 1;
+    }
+    const float* __restrict__ base = a.map + (size_t)b * a.nloc * a.NS;
+    const int k = k0 + warp;
+    for (int bi = blk_lo; bi < blk_hi; ++bi) {
+        const int t0 = bi << a.blk_shift;
+        __syncthreads();                                 // the previous block's tile has been consumed
+        for (int i = threadIdx.x; i < 16 * pitch; i += 256) {
+            const int rr = i / pitch, cc = i - rr * pitch;
+            const int kk = k0 - 4 + rr, tt = t0 - 4 + cc;
+            s_tile[i] = (kk >= 0 && kk < a.nloc && tt >= 0 && tt < a.N) ? base[(size_t)kk * a.NS + tt] : 0.f;
+        }
+        __syncthreads();
+        if (k < a.nloc) {
+            float v = -INFINITY;
+            int at = INT_MAX;
+            for (int j = lane; j < blk; j += 32) {       // ascending positions inside the lane
+                if (t0 + j >= a.N) break;
+                float sum = 0.f;
+#pragma unroll 1
+                for (int dk = 0; dk < 9; ++dk) {
+                    const float* __restrict__ row = s_tile + (warp + dk) * pitch + j;
+#pragma unroll
+                    for (int dt = 0; dt < 9; ++dt) sum = __fadd_rn(sum, row[dt]);
+                }
+                const float c = __fsub_rn(s_tile[(warp + 4) * pitch + j + 4], __fdiv_rn(sum, 81.f));
+                if (c > v) { v = c; at = t0 + j; }
+            }
+            warp_argmax(v, at);
+            if (lane == 0) {
+                const size_t o = ((size_t)b * a.nloc + k) * a.NB + bi;
+                a.nbm_val[o] = v;
+                a.nbm_pos[o] = at;
+            }
+        }
+    }
+    if (k < a.nloc) {                                    // row maximum over the row's (now current) block table
+        __syncwarp();
+        const size_t rowi = (size_t)b * a.nloc + k;
+        float v = -INFINITY;
+        int at = INT_MAX;
+        rescan_row(a.nbm_val + rowi * a.NB, a.nbm_pos + rowi * a.NB, a.NB, 0, 0, lane, v, at);
+        warp_argmax(v, at);
+        if (lane == 0) {
+            a.nrow_val[rowi] = v;
+            a.nrow_pos[rowi] = (at == INT_MAX) ? 0 : at;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------

@@ -290,6 +290,11 @@ static int launch_apply(Plan* p, int batch, const Best* winner, int step, int n_
     a.parity = (int)(p->iter & 1u);
     a.map = (SELECT && p->pos_free) ? p->map : nullptr;
     a.NS = p->NS;
+    if (SELECT && p->lcn) {            // select on the normalised tables, report the raw map value
+        a.row_val = p->nrow_val;
+        a.row_pos = p->nrow_pos;
+        a.raw_map = p->map;
+    }
     MPB_DISPATCH_M(p->M, {
         using F = BlockFft<MM, float>;
         const size_t smem = (size_t)(F::SMEM_CPX + 256) * sizeof(C32);
@@ -312,8 +317,42 @@ static void mark(Plan* p, int tag, cudaStream_t st) {
     p->ev_tag.push_back(tag);
 }
 
+// LCN selection: refresh the normalised block / row maxima from the resident raw map (whole rows after a full pass,
+// the winners' windows after a step).
+static int lcn_refresh(Plan* p, int batch, bool full, cudaStream_t st) {
+    LcnArgs l;
+    l.map = p->map;
+    l.upd = p->upd;
+    l.nbm_val = p->nbm_val;
+    l.nbm_pos = p->nbm_pos;
+    l.nrow_val = p->nrow_val;
+    l.nrow_pos = p->nrow_pos;
+    l.nloc = p->nloc;
+    l.N = p->N;
+    l.NS = p->NS;
+    l.NB = p->NB;
+    l.blk_shift = p->blk_shift;
+    l.A = p->A;
+    l.full = full ? 1 : 0;
+    const size_t smem = (size_t)16 * (p->blk + 8) * sizeof(float);
+    dim3 grid((p->nloc + 7) / 8, batch);
+    k_lcn_refresh<<<grid, 256, smem, st>>>(l);
+    MPB_LAUNCH_CHECK("k_lcn_refresh");
+    return MPB200_OK;
+}
+
+static int step_refresh_raw(Plan* p, int batch, cudaStream_t st);
+
 // Refresh the map / block maxima / row maxima after k_apply's subtraction.
 static int step_refresh(Plan* p, int batch, cudaStream_t st) {
+    const bool full_refresh = (p->mode == MPB200_MODE_GRAM || p->mode == MPB200_MODE_SGRAM) && p->refresh_every > 0 &&
+                              (p->iter + 1) % (unsigned)p->refresh_every == 0;
+    int rc = step_refresh_raw(p, batch, st);
+    if (!rc && p->lcn) rc = lcn_refresh(p, batch, full_refresh, st);
+    return rc;
+}
+
+static int step_refresh_raw(Plan* p, int batch, cudaStream_t st) {
     int rc = MPB200_OK;
     if (p->mode == MPB200_MODE_FULL) {
         rc = full_pass(p, batch, nullptr, st);
@@ -876,6 +915,28 @@ int mpb200_plan_set_option(mpb200_plan_t plan, int option, long long value) {
             p->delta_occ = 0;          // another kernel instantiation: re-query its occupancy
             p->cur_batch = 0;          // tables of a batch in flight were built under the other convention
             return MPB200_OK;
+        case MPB200_OPT_LOCAL_CONTRAST_NORM: {
+            if (value == 0) { p->lcn = false; p->cur_batch = 0; return MPB200_OK; }
+            if (p->mode != MPB200_MODE_GRAM && p->mode != MPB200_MODE_SGRAM)
+                return fail(MPB200_EINVAL, "local-contrast-norm selection needs a resident map (GRAM or SGRAM mode)");
+            if (p->lo != 0 || p->hi != p->K)
+                return fail(MPB200_EINVAL, "local-contrast-norm selection is not available on atom-sharded plans "
+                                           "(the 9x9 box spans shard boundaries)");
+            int rc = check_plan(p, false);
+            if (rc) return rc;
+            if (!p->nbm_val) {
+                rc = dev_alloc(p, &p->nbm_val, (size_t)p->Bcap * p->nloc * p->NB);
+                if (!rc) rc = dev_alloc(p, &p->nbm_pos, (size_t)p->Bcap * p->nloc * p->NB);
+                if (!rc) rc = dev_alloc(p, &p->nrow_val, (size_t)p->Bcap * p->nloc);
+                if (!rc) rc = dev_alloc(p, &p->nrow_pos, (size_t)p->Bcap * p->nloc);
+                if (rc) return rc;
+            }
+            p->lcn = true;
+            p->pos_free = false;       // the normalised tables carry exact positions
+            p->delta_occ = 0;
+            p->cur_batch = 0;
+            return MPB200_OK;
+        }
         case MPB200_OPT_FORCE_TABLES:
             p->force_tables = value != 0;
             return MPB200_OK;
@@ -921,7 +982,9 @@ int mpb200_begin(mpb200_plan_t plan, const float* signal, int batch, void* strea
     p->iter = 0;
     if (p->mode == MPB200_MODE_GRAM || p->mode == MPB200_MODE_SGRAM) {
         MPB_CUDA(cudaMemsetAsync(p->trunc_count, 0, 2 * sizeof(int), st));
-        return full_pass(p, batch, p->map, st, true);
+        rc = full_pass(p, batch, p->map, st, true);
+        if (!rc && p->lcn) rc = lcn_refresh(p, batch, true, st);
+        return rc;
     }
     return full_pass(p, batch, nullptr, st);
 }
@@ -931,6 +994,7 @@ int mpb200_local_best(mpb200_plan_t plan, mpb200_best* best, void* stream) {
     int rc = check_plan(p, true);
     if (rc) return rc;
     if (p->cur_batch < 1) return fail(MPB200_ESTATE, "mpb200_begin has not been called");
+    if (p->lcn) return fail(MPB200_ESTATE, "the step-wise interface does not offer local-contrast-norm selection");
     k_local_best<<<p->cur_batch, 256, 0, (cudaStream_t)stream>>>(p->row_val, p->row_pos, p->nloc, p->lo,
                                                                   reinterpret_cast<Best*>(best),
                                                                   p->pos_free ? p->map : nullptr, p->NS, p->N, p->blk_shift);

@@ -46,6 +46,13 @@ struct Plan {
     float* residual = nullptr;      // (Bmax, N)
     Best* best = nullptr;           // (Bmax)
 
+    // local-contrast-norm selection (MPB200_OPT_LOCAL_CONTRAST_NORM, map modes): second hierarchy over the normalised map
+    bool lcn = false;
+    float* nbm_val = nullptr;       // (Bcap, nloc, NB)
+    int* nbm_pos = nullptr;
+    float* nrow_val = nullptr;      // (Bcap, nloc)
+    int* nrow_pos = nullptr;
+
     // Gram mode
     float* gram = nullptr;          // (K, nloc, GS), GS = 2A
     float* map = nullptr;           // (Bmax, nloc, N)

@@ -112,6 +112,13 @@ class Plan:
         check(self._lib.mpb200_plan_set_option(self._h, 4, int(bool(on))), "mpb200_plan_set_option")
         return self
 
+    def set_local_contrast_norm(self, on: bool) -> "Plan":
+        """GRAM / SGRAM mode: select on ``fm - avg_pool2d(fm, 9x9)`` incrementally (include/mpb200.h,
+        MPB200_OPT_LOCAL_CONTRAST_NORM; modules/matchingpursuit.py:286-296)."""
+        check(self._lib.mpb200_plan_set_option(self._h, 5, int(bool(on))), "mpb200_plan_set_option")
+        self.local_contrast_norm = bool(on)
+        return self
+
     # ---- per-kernel timing (bench aid) ----------------------------------
     def timing(self, enable: bool) -> None:
         check(self._lib.mpb200_plan_timing_enable(self._h, int(bool(enable))), "mpb200_plan_timing_enable")

@@ -69,12 +69,24 @@ def get_plan(n_atoms: int, atom_size: int, n_samples: int, batch: int, device, m
         total = torch.cuda.get_device_properties(dev).total_memory
         _evict_until(dev.index, int(_PLAN_CACHE_FRACTION * total), _PLAN_CACHE_MAX - 1)
         try:
-            plan = Plan(n_atoms, atom_size, n_samples, batch, mode=mode, device=dev)
+            plan = _make_plan(n_atoms, atom_size, n_samples, batch, mode, dev)
         except MpbError:
             clear_plan_cache(dev.index)                           # make room (idle plans only) and try once more
-            plan = Plan(n_atoms, atom_size, n_samples, batch, mode=mode, device=dev)
+            plan = _make_plan(n_atoms, atom_size, n_samples, batch, mode, dev)
     _PLAN_CACHE[key] = plan                                       # (re)inserted last: most recently used
     return plan
+
+
+def _make_plan(n_atoms, atom_size, n_samples, batch, mode, dev) -> Plan:
+    """``mode="lcn"``: a plan whose selection is the incremental local-contrast-norm one -- it needs a resident map,
+    so a shape AUTO would code by windowed re-correlation is planned as SGRAM instead."""
+    if mode != "lcn":
+        return Plan(n_atoms, atom_size, n_samples, batch, mode=mode, device=dev)
+    plan = Plan(n_atoms, atom_size, n_samples, batch, mode="auto", device=dev)
+    if plan.mode not in ("gram", "sgram"):
+        plan.close()
+        plan = Plan(n_atoms, atom_size, n_samples, batch, mode="sgram", device=dev)
+    return plan.set_local_contrast_norm(True)
 
 
 def clear_plan_cache(dev_index: Optional[int] = None) -> None:
@@ -356,6 +368,15 @@ class _SparseCodeJob:
                          on_select=on_select if visit_key_point is not None else None,
                          local_contrast_norm=bool(local_contrast_norm))
 
+        # plain LCN selection (no per-step callback that must see the dense map): the engine's incremental form
+        if (dense is not None and local_contrast_norm and compute_feature_map is None and extract_atom_embedding is None
+                and visit_key_point is None and approx is None and not with_grad and plan is None
+                and atom_size <= engine.MAX_PLAN_ATOM and mode == "auto"):
+            try:
+                get_plan(n_atoms, atom_size, n_samples, batch, _work_device(signal, device), "lcn")
+                dense, mode = None, "lcn"
+            except MpbError:
+                pass                                                        # no resident map possible: dense schedule
         if with_grad:
             # Gradients are wanted: the greedy selection itself has none (torch.max passes gradient to the selected
             # entry only), so the engine finds the events and PyTorch re-evaluates values, scaled atoms and residual

@@ -585,3 +585,57 @@ def test_errors():
         plan.set_dictionary(torch.randn(5, 16))
     with pytest.raises(ValueError):
         mpb.sparse_code(torch.zeros(128, device=DEV), torch.randn(4, 16))   # not (B,C,N), as the reference
+
+
+# --------------------------------------------------------------------------
+# incremental local-contrast-norm selection (modules/matchingpursuit.py:286-296)
+# --------------------------------------------------------------------------
+LCN_CASES = [
+    # (K, A, N, B, S)
+    (12, 32, 512, 2, 16),
+    (40, 100, 3000, 2, 24),      # ragged sizes, blocks of 16 positions
+    (64, 256, 8192, 2, 30),
+    (5, 700, 2000, 1, 10),       # fewer atoms than the box is tall
+    (512, 512, 2 ** 15, 1, 24),  # experiments/e_2023_7_20's shape (512 x 512 dictionary)
+]
+
+
+@pytest.mark.parametrize("mode", ["sgram", "gram"])
+@pytest.mark.parametrize("case", LCN_CASES, ids=lambda c: "K%d_A%d_N%d_B%d_S%d" % c)
+def test_incremental_lcn_against_oracle(case, mode):
+    """The engine refreshes the normalised map only in the winner's window (+-4 columns) and keeps a second
+    block/row-max hierarchy on it; the oracle recomputes avg_pool2d over the whole map every step.  Noise signals:
+    truncated winners and near-ties are common.  The reported values are RAW map values (:296)."""
+    k, a, n, b, s = case
+    d = O.make_dictionary(k, a, seed=k + a)
+    sig = torch.cat([O.make_planted_signals(d, 1, n, max(4, s // 2), seed=n)] +
+                    ([O.make_noise_signals(b - 1, n, seed=n + 1)] if b > 1 else []), dim=0)
+    tr = O.greedy_pursuit(sig, d, s, local_contrast_norm=True, want_margin=True)
+    run, plan = plan_runner(d, n, b, mode)
+    plan.set_local_contrast_norm(True)
+    rep = resync_against_trace(run, sig.numpy(), tr)
+    plan.close()
+    assert rep.checked == rep.eligible and rep.checked >= 0.8 * rep.total, rep
+
+
+def test_lcn_dropin_takes_the_incremental_path_and_matches_the_dense_schedule():
+    k, a, n, b, s = 24, 64, 2048, 2, 14
+    d = O.make_dictionary(k, a, seed=31)
+    sig = O.make_planted_signals(d, b, n, 8, seed=32)
+    launches = mpb.lib().mpb200_launch_count()
+    flat, scatter, res = mpb.sparse_code(sig.to(DEV), d.to(DEV), s, flatten=True, return_residual=True,
+                                         local_contrast_norm=True)
+    fast = mpb.lib().mpb200_launch_count() - launches
+    seen = []
+    launches = mpb.lib().mpb200_launch_count()
+    flat2, _, res2 = mpb.sparse_code(sig.to(DEV), d.to(DEV), s, flatten=True, return_residual=True,
+                                     local_contrast_norm=True, visit_key_point=lambda fm, ai, p, at: seen.append(ai))
+    dense = mpb.lib().mpb200_launch_count() - launches
+    assert len(seen) == b * s
+    assert [(ai, j, int(p)) for ai, j, p, _ in flat] == [(ai, j, int(p)) for ai, j, p, _ in flat2]
+    np.testing.assert_allclose(res.cpu().numpy(), res2.cpu().numpy(), rtol=1e-4, atol=2e-6)
+    tr = O.greedy_pursuit(sig, d, s, local_contrast_norm=True, want_margin=True)
+    if (tr.margin.numpy() > MARGIN).all():
+        want = O.sparse_code(sig, d, s, flatten=True, local_contrast_norm=True)[0]
+        assert [(ai, j, int(p)) for ai, j, p, _ in flat] == [(ai, j, int(p)) for ai, j, p, _ in want]
+    assert fast < dense          # three launches per step instead of a dense map + 81-tap selection per step
