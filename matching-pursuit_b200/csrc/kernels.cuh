@@ -1295,44 +1295,61 @@ k_delta(const DeltaArgs a) {
             // only go to shared memory here -- the row warps publish them to bm_val / bm_pos.
             const int ntask = second ? 2 * nvb : nvb;
             if (blk >= 128 && start + (nvb << a.blk_shift) <= a.N) {   // whole blocks of 128 / 256: one / two float4 per lane
+                // A task is one block index of BOTH rows (they share every address but the row offset): two (blk 128)
+                // or four (blk 256) 16-byte loads, an fmax tree per row and one redux.sync.max per row on an
+                // order-preserving key.  DEFER: the two row warps have just re-derived a row maximum each and take the
+                // last (up to) two block indices, the other warps share the rest.
                 const float* __restrict__ rowl = st0 + 4 * lane;
                 const int sh = a.blk_shift;
-                // DEFER: the two row warps have just re-derived a row maximum each; they take the last (up to) four
-                // tasks, the other warps share the rest
-                const int nrt = DEFER ? min(ntask, 4) : 0;
-                const int t_first = !DEFER ? warp : (warp < RW0 ? warp : ntask - nrt + 2 * (warp - RW0));
-                const int t_end = !DEFER ? ntask : (warp < RW0 ? ntask - nrt : min(ntask, t_first + 2));
+                const int nrt = DEFER ? min(nvb, 2) : 0;
+                const int t_first = !DEFER ? warp : (warp < RW0 ? warp : nvb - nrt + (warp - RW0));
+                const int t_end = !DEFER ? nvb : (warp < RW0 ? nvb - nrt : min(nvb, t_first + 1));
                 const int t_step = !DEFER ? NW : (warp < RW0 ? RW0 : 1);
-                for (int task = t_first; task < t_end; task += t_step) {
-                    const int row1 = task >= nvb ? 1 : 0;
-                    const int slot = task + row1 * (32 - nvb);    // which * 32 + block
-                    const int o = row1 * a.cap + ((task - row1 * nvb) << sh);   // offset into the staging rows
-                    const float4 c0 = *reinterpret_cast<const float4*>(rowl + o);
-                    float4 c1 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-                    if (blk == 256) c1 = *reinterpret_cast<const float4*>(rowl + o + 128);
-                    float v = fmaxf(fmaxf(fmaxf(c0.x, c0.y), fmaxf(c0.z, c0.w)),
-                                    fmaxf(fmaxf(c1.x, c1.y), fmaxf(c1.z, c1.w)));
-                    const int kmax = __reduce_max_sync(0xffffffffu, float_key(v));
-                    v = __int_as_float(kmax ^ ((kmax >> 31) & 0x7fffffff));
-                    if (!(v == v)) v = -INFINITY;                 // a NaN in the map never wins (as in the comparison-based paths)
-                    if constexpr (NOPOS) {
-                        if (lane == 0) sBVw[slot] = make_float2(v, __int_as_float(start + ((slot & 31) << sh)));
-                        continue;
+                for (int i = t_first; i < t_end; i += t_step) {
+                    const float* __restrict__ p0 = rowl + (i << sh);
+                    const float4 c00 = *reinterpret_cast<const float4*>(p0);
+                    const float4 c10 = *reinterpret_cast<const float4*>(p0 + a.cap);
+                    float4 c01 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), c11 = c01;
+                    if (blk == 256) {
+                        c01 = *reinterpret_cast<const float4*>(p0 + 128);
+                        c11 = *reinterpret_cast<const float4*>(p0 + a.cap + 128);
                     }
-                    int at = INT_MAX;                             // descending order: the lowest matching position survives
-                    at = (c1.w + 0.0f == v) ? 131 : at;
-                    at = (c1.z + 0.0f == v) ? 130 : at;
-                    at = (c1.y + 0.0f == v) ? 129 : at;
-                    at = (c1.x + 0.0f == v) ? 128 : at;
-                    at = (c0.w + 0.0f == v) ? 3 : at;
-                    at = (c0.z + 0.0f == v) ? 2 : at;
-                    at = (c0.y + 0.0f == v) ? 1 : at;
-                    at = (c0.x + 0.0f == v) ? 0 : at;
-                    at = __reduce_min_sync(0xffffffffu, at == INT_MAX ? at : at + 4 * lane);
-                    // position = start + (block index within its row) * blk + at
-                    if (lane == 0)
-                        sBVw[slot] = make_float2(v, __int_as_float(at == INT_MAX ? INT_MAX
-                                                                                  : start + ((slot & 31) << sh) + at));
+                    float v0 = fmaxf(fmaxf(fmaxf(c00.x, c00.y), fmaxf(c00.z, c00.w)),
+                                     fmaxf(fmaxf(c01.x, c01.y), fmaxf(c01.z, c01.w)));
+                    float v1 = fmaxf(fmaxf(fmaxf(c10.x, c10.y), fmaxf(c10.z, c10.w)),
+                                     fmaxf(fmaxf(c11.x, c11.y), fmaxf(c11.z, c11.w)));
+                    const int k0 = __reduce_max_sync(0xffffffffu, float_key(v0));
+                    const int k1 = __reduce_max_sync(0xffffffffu, float_key(v1));
+                    v0 = __int_as_float(k0 ^ ((k0 >> 31) & 0x7fffffff));
+                    v1 = __int_as_float(k1 ^ ((k1 >> 31) & 0x7fffffff));
+                    if (!(v0 == v0)) v0 = -INFINITY;              // a NaN in the map never wins (as in the comparison-based paths)
+                    if (!(v1 == v1)) v1 = -INFINITY;
+                    const int pos0 = start + (i << sh);           // NOPOS: the block's start stands for the position
+                    if constexpr (NOPOS) {
+                        if (lane == 0) {
+                            sBVw[i] = make_float2(v0, __int_as_float(pos0));
+                            sBVw[32 + i] = make_float2(v1, __int_as_float(pos0));
+                        }
+                    } else {
+                        // first position of the maximum: descending order, so the lowest match survives
+                        auto first_at = [&](const float4& lo4, const float4& hi4, float v) {
+                            int at = INT_MAX;
+                            at = (hi4.w + 0.0f == v) ? 131 : at;
+                            at = (hi4.z + 0.0f == v) ? 130 : at;
+                            at = (hi4.y + 0.0f == v) ? 129 : at;
+                            at = (hi4.x + 0.0f == v) ? 128 : at;
+                            at = (lo4.w + 0.0f == v) ? 3 : at;
+                            at = (lo4.z + 0.0f == v) ? 2 : at;
+                            at = (lo4.y + 0.0f == v) ? 1 : at;
+                            at = (lo4.x + 0.0f == v) ? 0 : at;
+                            return __reduce_min_sync(0xffffffffu, at == INT_MAX ? at : at + 4 * lane);
+                        };
+                        const int at0 = first_at(c00, c01, v0), at1 = first_at(c10, c11, v1);
+                        if (lane == 0) {
+                            sBVw[i] = make_float2(v0, __int_as_float(at0 == INT_MAX ? INT_MAX : pos0 + at0));
+                            sBVw[32 + i] = make_float2(v1, __int_as_float(at1 == INT_MAX ? INT_MAX : pos0 + at1));
+                        }
+                    }
                 }
             } else if (blk <= 64 && start + (nvb << a.blk_shift) <= a.N) {
                 // short atoms (blocks of 16 / 32 / 64 positions, whole blocks inside the signal): a task is 64

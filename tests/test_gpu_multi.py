@@ -16,7 +16,7 @@ def _free_port() -> int:
         return s.getsockname()[1]
 
 
-def _worker(rank: int, world: int, port: int, exchange: str, out_dir: str):
+def _worker(rank: int, world: int, port: int, exchange: str, out_dir: str, mode: str = "recorrelate"):
     import torch.distributed as dist
     import matching_pursuit_b200 as mpb  # noqa: F401
     from matching_pursuit_b200.distributed import AtomShardedPursuit
@@ -28,23 +28,25 @@ def _worker(rank: int, world: int, port: int, exchange: str, out_dir: str):
     k, a, n, b, s = 37, 128, 4096, 3, 24
     d = O.make_dictionary(k, a, seed=5)
     sig = O.make_planted_signals(d, b, n, 12, seed=6)
-    pursuit = AtomShardedPursuit(k, a, n, b, device=dev, mode="recorrelate", exchange=exchange).set_dictionary(d)
+    pursuit = AtomShardedPursuit(k, a, n, b, device=dev, mode=mode, exchange=exchange).set_dictionary(d)
     atom, pos, val, res = pursuit.run(sig.to(dev), s)
     torch.cuda.synchronize()
     timed_out = pursuit.engine.plan.exchange_timed_out() if exchange == "p2p" else False
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), atom=atom.cpu().numpy(), pos=pos.cpu().numpy(),
              val=val.cpu().numpy(), res=res.cpu().numpy(), timed_out=timed_out)
+    pursuit.close()                       # collective: peers unmap the mailboxes before anybody frees one
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("mode", ["recorrelate", "sgram"])
 @pytest.mark.parametrize("exchange", ["p2p", "nccl"])
-def test_two_ranks_atom_sharded(exchange, tmp_path):
+def test_two_ranks_atom_sharded(exchange, mode, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     import torch.multiprocessing as mp
     from oracle import mp_oracle as O
     from parity import compare_with_oracle_trace
-    mp.spawn(_worker, args=(2, _free_port(), exchange, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), exchange, str(tmp_path), mode), nprocs=2, join=True)
     k, a, n, b, s = 37, 128, 4096, 3, 24
     d = O.make_dictionary(k, a, seed=5)
     sig = O.make_planted_signals(d, b, n, 12, seed=6)
@@ -53,4 +55,4 @@ def test_two_ranks_atom_sharded(exchange, tmp_path):
     assert not bool(r0["timed_out"]) and not bool(r1["timed_out"])
     for key in ("atom", "pos", "val", "res"):
         assert np.array_equal(r0[key], r1[key]), key
-    assert compare_with_oracle_trace(tr, r0["atom"], r0["pos"], r0["val"], r0["res"]) > 0
+    assert compare_with_oracle_trace(tr, r0["atom"], r0["pos"], r0["val"], r0["res"]) >= 0.9 * s * b
