@@ -42,6 +42,17 @@ __device__ __forceinline__ C32 ld_stream(const C32* p) {
     return {v.x, v.y};
 }
 
+// Programmatic dependent launch: the kernels of the iteration loop are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so a kernel may be scheduled while its predecessor in the
+// stream still runs.  Each of them first lets ITS successor be scheduled (launch_dependents: takes effect once every
+// CTA of this grid has issued it or exited, so the successor only fills what is left of the chip) and then waits
+// until the predecessor has completed and flushed its memory (wait) before touching anything it produced -- the
+// launch latency of the next kernel hides behind the current one.  Both are no-ops under an ordinary launch.
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // (value, index) ordering of torch.max over a flattened map: larger value
 // wins, equal values go to the lower index.
 __device__ __forceinline__ void take_better(float& v, int& i, float ov, int oi) {
@@ -303,6 +314,7 @@ template <int M, int MODE>
 __global__ void __launch_bounds__((BlockFft<M, float>::T < 256 ? 256 : BlockFft<M, float>::T),
                                   ((MODE & MODE_DENSE) ? MPB_CORR_MINB_DENSE : MPB_CORR_MINB))
 k_corr(const CorrArgs a) {
+    pdl_prologue();
     if (a.skip && *a.skip) return;
     using F = BlockFft<M, float>;
     constexpr int TPB = F::T < 256 ? 256 : F::T;
@@ -705,7 +717,8 @@ k_apply(const ApplyArgs a) {
     C32* stw2 = sm + F::SMEM_CPX;
     __shared__ Best s_best;
     const int b = blockIdx.x;
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) stw2[i] = a.tw2[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) stw2[i] = a.tw2[i];     // constant table: before the wait
+    pdl_prologue();
     Best w;
     if constexpr (SELECT) {
         w = block_best(a.row_val, a.row_pos, b, a.nloc, a.atom_lo, &s_best);
@@ -821,6 +834,7 @@ k_gram_update(const GramArgs a) {
     constexpr int BPC = BLK >= 128 ? 1 : 128 / BLK;        // blocks per chunk
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+    pdl_prologue();
     if (row >= a.rows) return;
     const int b = row / a.nloc, j = row - b * a.nloc;
     const GramUpdate u = a.upd[b];
@@ -1081,6 +1095,7 @@ k_delta(const DeltaArgs a) {
     const int warp = tl >> 5, lane = tl & 31;
     const int which0 = warp - RW0;                       // row (0/1) this warp re-derives; outside [0, 2): none
     unsigned phase = 0;
+    pdl_prologue();                                      // the table above is constant; everything below is not
     __syncthreads();
 
     // Work items (pair group g, signal b), g-major so that a CTA keeps its pair spectra hot; the
@@ -1648,6 +1663,7 @@ k_lcn_refresh(const LcnArgs a) {
     const int b = blockIdx.y, k0 = blockIdx.x * 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int blk = 1 << a.blk_shift, pitch = blk + 8;
+    pdl_prologue();
     int blk_lo = 0, blk_hi = a.NB;                       // blocks [blk_lo, blk_hi) are refreshed
     if (!a.full) {
         const int p = a.upd[b].position;

@@ -40,6 +40,10 @@ int fail(int code, const std::string& msg) {
             return fail(MPB200_ECUDA, std::string("launch ") + name + ": " + cudaGetErrorString(_e)); \
     } while (0)
 
+#ifndef MPB_PDL
+#define MPB_PDL 1     // programmatic dependent launch of the iteration-loop kernels (0: ordinary stream order)
+#endif
+
 #define MPB_DISPATCH_M(m, ...)                                            \
     switch (m) {                                                          \
         case 512: { constexpr int MM = 512; __VA_ARGS__; } break;         \
@@ -67,6 +71,23 @@ static cudaError_t allow_smem(K kernel, size_t bytes) {
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e == cudaSuccess) granted[key] = bytes;
     return e;
+}
+
+// Launch of an iteration-loop kernel (one struct argument) with programmatic stream serialisation allowed: it may be
+// scheduled while its predecessor still runs and waits for it on the device (kernels.cuh, pdl_prologue).
+template <typename Arg>
+static cudaError_t launch_pdl(void (*kernel)(Arg), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const Arg& arg) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = MPB_PDL;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, arg);
 }
 
 // ---------------------------------------------------------------------------
@@ -158,7 +179,7 @@ static int launch_window_fft(Plan* p, const float* src, long long row_stride, in
 }
 
 template <int MODE>
-static int launch_corr(Plan* p, CorrArgs a, int groups, cudaStream_t st) {
+static int launch_corr(Plan* p, CorrArgs a, int groups, cudaStream_t st, bool pdl = false) {
     if (a.nwin <= 0) return MPB200_OK;
     a.bm_cap = p->bm_cap;
     MPB_DISPATCH_M(p->M, {
@@ -169,7 +190,8 @@ static int launch_corr(Plan* p, CorrArgs a, int groups, cudaStream_t st) {
         if (MPB_CORR_SEP && (MODE & MODE_ROWMAX) != 0) smem += (size_t)NT * (p->bm_cap + 64) * sizeof(float2);
         MPB_CUDA(allow_smem(k_corr<MM, MODE>, smem));
         dim3 grid((a.npairs + NT - 1) / NT, groups);
-        k_corr<MM, MODE><<<grid, TPB, smem, st>>>(a);
+        if (pdl) MPB_CUDA(launch_pdl(k_corr<MM, MODE>, grid, dim3(TPB), smem, st, a));
+        else k_corr<MM, MODE><<<grid, TPB, smem, st>>>(a);
     });
     MPB_LAUNCH_CHECK("k_corr");
     return MPB200_OK;
@@ -299,7 +321,7 @@ static int launch_apply(Plan* p, int batch, const Best* winner, int step, int n_
         using F = BlockFft<MM, float>;
         const size_t smem = (size_t)(F::SMEM_CPX + 256) * sizeof(C32);
         MPB_CUDA((allow_smem(k_apply<MM, SELECT>, smem)));
-        k_apply<MM, SELECT><<<batch, 256, smem, st>>>(a);
+        MPB_CUDA(launch_pdl(k_apply<MM, SELECT>, dim3(batch), dim3(256), smem, st, a));
     });
     MPB_LAUNCH_CHECK("k_apply");
     return MPB200_OK;
@@ -336,7 +358,7 @@ static int lcn_refresh(Plan* p, int batch, bool full, cudaStream_t st) {
     l.full = full ? 1 : 0;
     const size_t smem = (size_t)16 * (p->blk + 8) * sizeof(float);
     dim3 grid((p->nloc + 7) / 8, batch);
-    k_lcn_refresh<<<grid, 256, smem, st>>>(l);
+    MPB_CUDA(launch_pdl(k_lcn_refresh, grid, dim3(256), smem, st, l));
     MPB_LAUNCH_CHECK("k_lcn_refresh");
     return MPB200_OK;
 }
@@ -398,7 +420,7 @@ static int step_refresh_raw(Plan* p, int batch, cudaStream_t st) {
                 if (items >= (1LL << 31)) return fail(MPB200_EINVAL, "SGRAM: more than 2^31 (pair, signal) work items per launch");
                 long long ctas = (long long)p->sm_count * p->delta_occ;
                 if (ctas > items) ctas = items;
-                kernel<<<(unsigned)ctas, TPB, smem, st>>>(d);
+                MPB_CUDA(launch_pdl(kernel, dim3((unsigned)ctas), dim3(TPB), smem, st, d));
             });
             MPB_LAUNCH_CHECK("k_delta");
             mark(p, 4, st);
@@ -411,7 +433,7 @@ static int step_refresh_raw(Plan* p, int batch, cudaStream_t st) {
             a.dense_atom_stride = p->NS;
             a.dense_col_off = 0;
             a.pos_free = p->pos_free ? 1 : 0;
-            rc = launch_corr<MODE_DENSE | MODE_BLOCKMAX | MODE_ROWMAX>(p, a, trunc_groups(p, batch), st);
+            rc = launch_corr<MODE_DENSE | MODE_BLOCKMAX | MODE_ROWMAX>(p, a, trunc_groups(p, batch), st, true);
         }
     } else if (p->mode == MPB200_MODE_GRAM) {
         const bool refresh = p->refresh_every > 0 && (p->iter + 1) % (unsigned)p->refresh_every == 0;
@@ -434,11 +456,11 @@ static int step_refresh_raw(Plan* p, int batch, cudaStream_t st) {
             g.A = p->A;
             g.GS = p->GS;
             switch (p->blk) {
-                case 16: k_gram_update<16><<<(g.rows + 7) / 8, 256, 0, st>>>(g); break;
-                case 32: k_gram_update<32><<<(g.rows + 7) / 8, 256, 0, st>>>(g); break;
-                case 64: k_gram_update<64><<<(g.rows + 7) / 8, 256, 0, st>>>(g); break;
-                case 128: k_gram_update<128><<<(g.rows + 7) / 8, 256, 0, st>>>(g); break;
-                case 256: k_gram_update<256><<<(g.rows + 7) / 8, 256, 0, st>>>(g); break;
+                case 16: MPB_CUDA(launch_pdl(k_gram_update<16>, dim3((g.rows + 7) / 8), dim3(256), 0, st, g)); break;
+                case 32: MPB_CUDA(launch_pdl(k_gram_update<32>, dim3((g.rows + 7) / 8), dim3(256), 0, st, g)); break;
+                case 64: MPB_CUDA(launch_pdl(k_gram_update<64>, dim3((g.rows + 7) / 8), dim3(256), 0, st, g)); break;
+                case 128: MPB_CUDA(launch_pdl(k_gram_update<128>, dim3((g.rows + 7) / 8), dim3(256), 0, st, g)); break;
+                case 256: MPB_CUDA(launch_pdl(k_gram_update<256>, dim3((g.rows + 7) / 8), dim3(256), 0, st, g)); break;
                 default: return fail(MPB200_EINVAL, "unsupported block size");
             }
             MPB_LAUNCH_CHECK("k_gram_update");
@@ -452,13 +474,13 @@ static int step_refresh_raw(Plan* p, int batch, cudaStream_t st) {
             a.dense_row_stride = (long long)p->nloc * p->N;
             a.dense_atom_stride = p->N;
             a.dense_col_off = 0;
-            rc = launch_corr<MODE_DENSE | MODE_BLOCKMAX | MODE_ROWMAX>(p, a, trunc_groups(p, batch), st);
+            rc = launch_corr<MODE_DENSE | MODE_BLOCKMAX | MODE_ROWMAX>(p, a, trunc_groups(p, batch), st, true);
         }
     } else {
         CorrArgs a = base_corr_args(p);
         a.win = p->win_step;
         a.nwin = batch;
-        rc = launch_corr<MODE_BLOCKMAX | MODE_ROWMAX>(p, a, corr_groups(p, batch), st);
+        rc = launch_corr<MODE_BLOCKMAX | MODE_ROWMAX>(p, a, corr_groups(p, batch), st, true);
     }
     p->iter++;
     return rc;
