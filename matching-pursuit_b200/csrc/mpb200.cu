@@ -40,6 +40,9 @@ int fail(int code, const std::string& msg) {
             return fail(MPB200_ECUDA, std::string("launch ") + name + ": " + cudaGetErrorString(_e)); \
     } while (0)
 
+#ifndef MPB_GRAM_BATCH_FACTOR
+#define MPB_GRAM_BATCH_FACTOR 64     // AUTO takes the Gram table when max_batch * this >= n_atoms (and it fits)
+#endif
 #ifndef MPB_PDL
 #define MPB_PDL 1     // programmatic dependent launch of the iteration-loop kernels (0: ordinary stream order)
 #endif
@@ -682,11 +685,12 @@ int mpb200_plan_create(mpb200_plan_t* out, int n_atoms, int atom_size, int n_sam
     if (cap > max_batch) cap = max_batch;
     const bool sgram_ok = M2 <= 8192 && nvb_max <= 30 && cap >= 1;
     if (mode == MPB200_MODE_AUTO) {
-        // GRAM when the table and the resident map fit AND the table build (K window transforms per
-        // pair) is amortised by the batch: break-even is about K / max_batch iterations.
+        // GRAM when the table and the resident map fit AND the table build (K window transforms per pair, once per
+        // dictionary: skipped when the next call brings the same dictionary) is amortised by the batch.  Measured at
+        // configs[3]'s bands (1024 x 128, 16 signals): MPB_GRAM_BATCH_FACTOR, see profiles/r2_bench_c4_multiband_1gpu.json.
         const uint64_t budget = gram_budget_bytes ? gram_budget_bytes : (uint64_t)(0.4 * (double)free_b);
         const bool fits = gram_bytes <= budget && gram_bytes + map_bytes <= (uint64_t)(0.8 * (double)free_b);
-        if (fits && (long long)max_batch * 16 >= n_atoms && nvb_max <= 32) mode = MPB200_MODE_GRAM;
+        if (fits && (long long)max_batch * MPB_GRAM_BATCH_FACTOR >= n_atoms && nvb_max <= 32) mode = MPB200_MODE_GRAM;
         // SGRAM against windowed re-correlation, measured: 46 vs 63 us per atom-step at 32 x 2048 (pair, signal)
         // work items, 268 vs 341 us at 1 x 8192, 58.5 vs 62.7 us per iteration at 1 x 1024 (one rank of configs[4]
         // on 8 GPUs).  Below about a thousand items the persistent grid is mostly empty and the resident map

@@ -105,27 +105,67 @@ def _work_device(signal: torch.Tensor, device=None) -> torch.device:
 # --------------------------------------------------------------------------
 # events
 # --------------------------------------------------------------------------
+def _materialising(name):
+    """A list method that first turns a lazy EventList into the real list of tuples."""
+    base = getattr(list, name)
+
+    def method(self, *args, **kwargs):
+        self._fill()
+        return base(self, *args, **kwargs)
+    method.__name__ = name
+    return method
+
+
 class EventList(list):
-    """A list of reference-format event tuples ``(atom:int, batch:int,
-    pos: int64 (1,1), scaled_atom: float32 (1,1,A))`` that also carries the
-    packed arrays it was built from, so decoders can skip re-packing."""
-    packed = None  # (atom int64 (E,), batch int64 (E,), pos int64 (E,), rows float32 (E,A)) in list order
+    """A list of reference-format event tuples ``(atom:int, batch:int, pos: int64 (1,1), scaled_atom: float32
+    (1,1,A))`` (modules/matchingpursuit.py:305-321) that carries the packed arrays it stands for: ``packed = (atom
+    int64 (E,), batch int64 (E,), pos int64 (E,), rows float32 (E, A))`` in list order.
+
+    The tuples are built ON FIRST ACCESS: decoders, the multi-band conversions and the dictionary update work on
+    ``packed`` and never need them, and materialising B*S Python tuples with two tensor views each costs more than
+    the pursuit for small dictionaries.  Until then ``len()`` answers from the arrays; any other list operation --
+    iteration, indexing, slicing, comparison, mutation, concatenation, pickling -- materialises first, after which
+    this is an ordinary list."""
+    packed = None
+    _lazy = False
+
+    @classmethod
+    def from_packed(cls, atom, batch_idx, pos, rows) -> "EventList":
+        out = cls()
+        out.packed = (atom, batch_idx, pos, rows)
+        out._lazy = atom.numel() > 0
+        return out
+
+    def _fill(self) -> None:
+        if self._lazy:
+            self._lazy = False
+            atom, batch_idx, pos, rows = self.packed
+            n = atom.numel()
+            # one unbind per array instead of two Python-level indexing calls per event
+            list.extend(self, zip(atom.tolist(), batch_idx.tolist(), pos.view(n, 1, 1).unbind(0),
+                                  rows.view(n, 1, 1, rows.shape[-1]).unbind(0)))
+
+    def __len__(self):
+        return self.packed[0].numel() if self._lazy else list.__len__(self)
+
+    def __reduce_ex__(self, protocol):
+        self._fill()
+        return (list, (list(self),))
+
+
+for _name in ("__iter__", "__getitem__", "__setitem__", "__delitem__", "__contains__", "__reversed__", "__add__",
+              "__iadd__", "__mul__", "__rmul__", "__imul__", "__eq__", "__ne__", "__lt__", "__le__", "__gt__", "__ge__",
+              "__repr__", "append", "extend", "insert", "pop", "remove", "index", "count", "sort", "reverse", "copy",
+              "clear"):
+    setattr(EventList, _name, _materialising(_name))
+EventList.__hash__ = None
 
 
 def _events_from_packed(atom: torch.Tensor, batch_idx: torch.Tensor, pos: torch.Tensor,
                         rows: torch.Tensor) -> EventList:
-    """Tuples in the order given.  ``atom``/``batch_idx`` int64 (E,), ``pos``
-    int64 (E,), ``rows`` (E, A) on the output device."""
-    a_host = atom.tolist()
-    b_host = batch_idx.tolist()
-    a_size = rows.shape[1]
-    # one unbind per array instead of two Python-level indexing calls per event (the tuples are the reference's
-    # format, modules/matchingpursuit.py:305-321; building them dominated small-dictionary calls)
-    pos_views = pos.view(-1, 1, 1).unbind(0) if len(a_host) else ()
-    row_views = rows.view(-1, 1, 1, a_size).unbind(0) if len(a_host) else ()
-    out = EventList(zip(a_host, b_host, pos_views, row_views))
-    out.packed = (atom, batch_idx, pos, rows)
-    return out
+    """The event list of the given packed arrays (tuples in the order given, built on first access).
+    ``atom``/``batch_idx``/``pos`` int64 (E,), ``rows`` (E, A) on the output device."""
+    return EventList.from_packed(atom, batch_idx, pos, rows)
 
 
 def _first_seen_grouping(atom_step_major: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
@@ -335,7 +375,8 @@ class _SparseCodeJob:
     collect any."""
 
     def __init__(self, signal, d, n_steps, device, approx, flatten, extract_atom_embedding, visit_key_point,
-                 return_residual, local_contrast_norm, return_sparse_feature_map, compute_feature_map, mode, plan):
+                 return_residual, local_contrast_norm, return_sparse_feature_map, compute_feature_map, mode, plan,
+                 out_device=None):
         batch, channels, time = signal.shape
         if channels != 1:
             raise NotImplementedError("multi-channel signals fail in the reference's scatter_segments "
@@ -343,7 +384,9 @@ class _SparseCodeJob:
         self.with_grad = with_grad = _needs_grad(signal, d)
         self.batch, self.n_samples, self.n_steps = batch, time, n_steps
         self.n_atoms, self.atom_size = n_atoms, atom_size = d.shape[0], d.shape[-1]
-        self.out_dev = signal.device
+        # results live on the signal's device, unless the caller staged a host signal on the GPU itself and says
+        # where they belong (`out_device`: the multi-band codec uploads a host batch once instead of once per band)
+        self.out_dev = signal.device if out_device is None else torch.device(out_device)
         self.flatten, self.return_residual = flatten, return_residual
         self.return_sparse_feature_map = return_sparse_feature_map
         self.want_embeddings = extract_atom_embedding is not None
@@ -439,10 +482,8 @@ class _SparseCodeJob:
             start = 0
             for ai in seen_order.tolist():
                 c = int(counts[ai])
-                group = EventList(flattened[start:start + c])
-                group.packed = (g_atom[start:start + c], g_batch[start:start + c], g_pos[start:start + c],
-                                g_rows[start:start + c])
-                instances[ai] = group
+                instances[ai] = EventList.from_packed(g_atom[start:start + c], g_batch[start:start + c],
+                                                      g_pos[start:start + c], g_rows[start:start + c])
                 start += c
             return instances, scatter_segments
         if self.return_residual:                                             # :337-339
@@ -473,12 +514,12 @@ def sparse_code(signal, d, n_steps=100, device=None, approx=None, flatten=False,
 def sparse_code_start(signal, d, n_steps=100, device=None, approx=None, flatten=False, extract_atom_embedding=None,
                       visit_key_point=None, return_residual=False, local_contrast_norm=False,
                       return_sparse_feature_map=False, compute_feature_map=None, fft_convolution=False, *,
-                      mode: str = "auto", plan: Optional[Plan] = None) -> _SparseCodeJob:
+                      mode: str = "auto", plan: Optional[Plan] = None, out_device=None) -> _SparseCodeJob:
     """:func:`sparse_code` without the wait: the device work is enqueued on the current stream and the returned
-    job's ``result()`` gives what :func:`sparse_code` returns."""
+    job's ``result()`` gives what :func:`sparse_code` returns (on ``out_device`` when given, else on the signal's)."""
     return _SparseCodeJob(signal, d, n_steps, device, approx, flatten, extract_atom_embedding, visit_key_point,
                           return_residual, local_contrast_norm, return_sparse_feature_map, compute_feature_map, mode,
-                          plan)
+                          plan, out_device=out_device)
 
 
 def sparse_code_arrays(signal, d, n_steps=100, *, approx=None, mode: str = "auto", plan: Optional[Plan] = None,

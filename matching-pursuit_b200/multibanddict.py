@@ -34,10 +34,27 @@ GlobalEventTuple = Tuple[int, int, float, float]
 BandEncodingPackage = Tuple[List[LocalEventTuple], Callable, Shape]
 
 
-class GlobalEventList(list):
-    """A list of GlobalEventTuples that also carries them as arrays: ``packed = (global atom int64 (E,),
-    batch int64 (E,), unit time float32 (E,), amplitude float32 (E,))`` in list order."""
-    packed = None
+class GlobalEventList(EventList):
+    """A list of GlobalEventTuples ``(global atom, batch, unit time (1,1) tensor, amplitude 0-d tensor)`` that carries
+    them as arrays: ``packed = (global atom int64 (E,), batch int64 (E,), unit time float32 (E,), amplitude float32
+    (E,))`` in list order; like :class:`EventList` the tuples are built on first access."""
+
+    def _fill(self) -> None:
+        if self._lazy:
+            self._lazy = False
+            atom, batch, time, amp = self.packed
+            list.extend(self, zip(atom.tolist(), batch.tolist(), time.view(-1, 1, 1).unbind(0), amp.unbind(0)))
+
+
+class _LocalEventList(EventList):
+    """Local tuples as ``to_local_tuple`` makes them (modules/multibanddict.py:219-235): the position is a Python
+    int and the atom a plain (A,) tensor."""
+
+    def _fill(self) -> None:
+        if self._lazy:
+            self._lazy = False
+            local, batch, pos, rows = self.packed
+            list.extend(self, zip(local.tolist(), batch.tolist(), pos.tolist(), rows.unbind(0)))
 
 
 def _packed_local(events, atom_size: int):
@@ -175,9 +192,9 @@ class BandSpec(object):
         pos = (unit_time * self.size).to(torch.int64)                        # int(): truncation towards zero
         d = self.d
         rows = d[local.to(d.device)] * amplitude.to(d.device).reshape(-1, 1)
-        a_host, b_host, p_host = local.tolist(), batch.tolist(), pos.tolist()
-        out = EventList(zip(a_host, b_host, p_host, rows.unbind(0)))
+        out = _LocalEventList()
         out.packed = (local, batch, pos, rows)
+        out._lazy = local.numel() > 0
         return out
 
     def to_global_tuple(self, event: LocalEventTuple, offset: int) -> GlobalEventTuple:   # :204-217
@@ -190,11 +207,12 @@ class BandSpec(object):
         local_index = self.to_local_atom_index(global_index, offset)
         return (local_index, batch, self.to_sample_time(unit_time), self.get_atom(local_index, amplitude))
 
-    def encode_start(self, batch, steps=16, extract_embeddings=None):
+    def encode_start(self, batch, steps=16, extract_embeddings=None, out_device=None):
         """Enqueue this band's pursuit on the current stream; ``encode_finish`` collects it."""
         return sparse_code_start(batch, self.d, steps, device=self.device, approx=self.slce, flatten=True,
                                  extract_atom_embedding=extract_embeddings,
-                                 local_contrast_norm=self.local_contrast_norm), batch.shape, bool(extract_embeddings)
+                                 local_contrast_norm=self.local_contrast_norm,
+                                 out_device=out_device), batch.shape, bool(extract_embeddings)
 
     @staticmethod
     def encode_finish(started) -> BandEncodingPackage:
@@ -279,15 +297,17 @@ class MultibandDictionaryLearning(object):
     def encode(self, batch, steps, extract_embeddings=None) -> Dict[int, BandEncodingPackage]:   # :399-404
         """The bands are independent pursuits: each is enqueued on its own stream behind the band split, and only
         then are the results collected (the reference's serial loop over the bands, run concurrently)."""
-        bands = fft_frequency_decompose(batch, self.min_size)
         dev = batch.device if batch.is_cuda else engine._require_cuda(None)
+        # a host batch is uploaded ONCE and split on the device; the results go back to the batch's own device
+        staged = batch if batch.is_cuda else batch.to(dev, non_blocking=True)
+        bands = fft_frequency_decompose(staged, self.min_size)
         main = torch.cuda.current_stream(dev)
         started = OrderedDict()
         for i, (size, band) in enumerate(self.bands.items()):
             side = self._stream(dev, i)
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                started[size] = band.encode_start(bands[size], steps, extract_embeddings)
+                started[size] = band.encode_start(bands[size], steps, extract_embeddings, out_device=batch.device)
         out = OrderedDict((size, BandSpec.encode_finish(job)) for size, job in started.items())
         for i in range(len(self.bands)):
             main.wait_stream(self._stream(dev, i))
@@ -318,8 +338,8 @@ class MultibandDictionaryLearning(object):
         if not parts:
             return out
         atom, batch, time, amp = (torch.cat([p[i] for p in parts]) for i in range(4))
-        out.extend(zip(atom.tolist(), batch.tolist(), time.view(-1, 1, 1).unbind(0), amp.unbind(0)))
         out.packed = (atom, batch, time, amp)
+        out._lazy = atom.numel() > 0
         return out
 
     def hierarchical_event_tuples(self, encoding: List[GlobalEventTuple],

@@ -7,6 +7,7 @@ import sys
 
 import numpy as np
 import pytest
+import torch
 from hypothesis import given, settings, strategies as st
 
 import matching_pursuit_b200 as mpb
@@ -106,3 +107,35 @@ int main() {
     csrc = os.path.join(os.path.dirname(os.path.abspath(mpb.__file__)), "csrc")
     subprocess.run(["g++", "-std=c++17", "-O1", "-I", csrc, str(src), "-o", str(exe)], check=True)
     assert subprocess.run([str(exe)], capture_output=True, text=True).stdout.strip() == "ok"
+
+
+def test_event_lists_materialise_on_first_access():
+    """Event lists carry packed arrays and build the reference's tuples (modules/matchingpursuit.py:305-321) only
+    when somebody looks at them; until then len() answers from the arrays, afterwards they are ordinary lists."""
+    import copy
+    import pickle
+    from matching_pursuit_b200.matchingpursuit import EventList, flatten_atom_dict
+    e, a = 5, 4
+
+    def make():
+        return EventList.from_packed(torch.arange(e), torch.zeros(e, dtype=torch.int64), torch.arange(e) * 10,
+                                     torch.randn(e, a))
+
+    ev = make()
+    assert isinstance(ev, list) and len(ev) == 5 and ev._lazy and bool(ev)
+    item = ev[2]
+    assert not ev._lazy and item[0] == 2 and item[1] == 0 and int(item[2]) == 20
+    assert item[2].shape == (1, 1) and item[2].dtype == torch.int64 and item[3].shape == (1, 1, a)
+    assert [x[0] for x in make()] == [0, 1, 2, 3, 4]
+    grown = []
+    grown.extend(make())
+    assert len(grown) == 5 and len(make()[1:3]) == 2 and len(make() + [1]) == 6 and len(list(make())) == 5
+    assert len(pickle.loads(pickle.dumps(make()))) == 5 and len(copy.copy(make())) == 5
+    assert len(flatten_atom_dict({1: make(), 2: make()})) == 10
+    assert len(sorted(make(), key=lambda x: -x[0])) == 5
+    mutated = make()
+    mutated.append("x")
+    assert len(mutated) == 6 and mutated[-1] == "x"
+    z = torch.zeros(0, dtype=torch.int64)
+    empty = EventList.from_packed(z, z, z, torch.zeros(0, a))
+    assert len(empty) == 0 and not empty and list(empty) == []
