@@ -313,6 +313,75 @@ struct BlockFft {
         });
     }
 
+    // ------------------------------------------------------------------------------------------------------------
+    // "Local first exchange" form (M = 4096, 256 threads x 16 values): the inputs are dealt to the threads so that the
+    // exchange between pass 1 and pass 2 stays inside a HALF-WARP -- 16 consecutive lanes trade 16 x 16 values through
+    // their own 272-entry region of the buffer and need a __syncwarp(), not a CTA barrier -- which leaves ONE CTA
+    // barrier per transform (between pass 2 and pass 3) instead of two.
+    //   thread tl:  x = tl & 15, j3 = tl >> 4  holds inputs  j1*256 + c,  c = x*16 + j3   (the caller's tables are
+    //               stored in that order: in_index_local; a spectrum staged in the buffer sits at slot_addr_local)
+    //   buffer:     P(a, b, j3) = j3*XS + a*S + b      a = m1,  b = x (before pass 2) or m2 (after)
+    //   pass 1      stores P(m1, x, j3), m1 = 0..15            (lanes of a half-warp: consecutive b)
+    //   pass 2      thread tl: m1 = tl & 15, j3 = tl >> 4; loads P(m1, x, j3), x = 0..15 (same half-warp's region),
+    //               stores its outputs IN PLACE: P(m1, m2, j3)  (lanes: stride S, odd -> conflict free)
+    //   pass 3      thread tl: m1 = tl & 15, m2 = tl >> 4; loads P(m1, m2, j3), j3 = 0..15; outputs as in pass3:
+    //               r[m3] = out[tl + (M/16)*m3]
+    // ------------------------------------------------------------------------------------------------------------
+    static constexpr bool HAS_LOCAL = (R1 == 16 && E == 16);
+    static MPB_HD int P(int a, int b, int j3) { return j3 * XS + a * S + b; }
+    static MPB_HD int in_index_local(int tl, int e) { return e * 256 + ((tl & 15) * 16 + (tl >> 4)); }
+    static MPB_HD int slot_addr_local(int tl, int e) { return P(e, tl & 15, tl >> 4); }
+    // where the local form keeps input bin j = j1*256 + c of a staged spectrum / the position of bin j in a table
+    // stored in the local form's load order (thread-major: entry j1*256 + tl is thread tl's j1-th input)
+    static MPB_HD int bin_addr_local(int j) { const int c = j & 255; return P(j >> 8, c >> 4, c & 15); }
+    static MPB_HD int table_index_local(int j) { const int c = j & 255; return (j & ~255) | ((c & 15) << 4) | (c >> 4); }
+
+    template <int DIR>
+    static MPB_HD void pass1_local(C* r, int tl, C* sm, const C* __restrict__ tw1) {
+        static_assert(HAS_LOCAL, "the local-exchange form exists for M = 4096 only");
+        const int x = tl & 15, j3 = tl >> 4, c = x * 16 + j3;
+        Dft<16, DIR, Real>::run(r);
+        C z = tw1[256 + c];
+        if constexpr (DIR < 0) z.y = -z.y;
+        C zp[16];
+        powers<16>(z, zp);
+        sm[P(0, x, j3)] = r[0];
+        static_for<1, 16>([&](auto m1c) {
+            constexpr int m1 = decltype(m1c)::value;
+            sm[P(m1, x, j3)] = cmul(r[m1], zp[m1]);
+        });
+    }
+
+    template <int DIR>
+    static MPB_HD void pass2_local(C* r, int tl, C* sm, const C* __restrict__ tw2) {
+        const int m1 = tl & 15, j3 = tl >> 4;
+        static_for<0, 16>([&](auto xc) {
+            constexpr int x = decltype(xc)::value;
+            r[x] = sm[P(m1, x, j3)];
+        });
+        Dft<16, DIR, Real>::run(r);
+        static_for<0, 16>([&](auto m2c) {
+            constexpr int m2 = decltype(m2c)::value;
+            C v = r[m2];
+            if constexpr (m2 > 0) {
+                C w = tw2[m2 * 16 + j3];
+                if constexpr (DIR < 0) w.y = -w.y;
+                v = cmul(v, w);
+            }
+            sm[P(m1, m2, j3)] = v;
+        });
+    }
+
+    template <int DIR>
+    static MPB_HD void pass3_local(C* r, int tl, const C* sm) {
+        const int m1 = tl & 15, m2 = tl >> 4;
+        static_for<0, 16>([&](auto jc) {
+            constexpr int j3 = decltype(jc)::value;
+            r[j3] = sm[P(m1, m2, j3)];
+        });
+        Dft<16, DIR, Real>::run(r);
+    }
+
     // afterwards r[u*16 + m3] = out[(tl + T*u) + (M/16)*m3]
     template <int DIR>
     static MPB_HD void pass3(C* r, int tl, const C* sm) {

@@ -175,7 +175,8 @@ __global__ void k_unit_norm(const float* __restrict__ x, float* __restrict__ y, 
 // ---------------------------------------------------------------------------
 // Spectra of atom pairs.  pair q of this plan = atoms (atom_lo + 2q, atom_lo + 2q + 1).
 // ---------------------------------------------------------------------------
-template <int M, typename Real>
+// LOCAL: the table is stored in the load order of BlockFft's local-first-exchange form (table_index_local).
+template <int M, typename Real, bool LOCAL = false>
 __global__ void __launch_bounds__(BlockFft<M, Real>::T)
 k_pair_spectra(const float* __restrict__ dict, int A, int atom_lo, int atom_hi,
                const cpx<Real>* __restrict__ tw1, const cpx<Real>* __restrict__ tw2, C32* __restrict__ pairspec,
@@ -208,7 +209,8 @@ k_pair_spectra(const float* __restrict__ dict, int A, int atom_lo, int atom_hi,
     const Real scale = (Real)1 / (Real)M;
 #pragma unroll
     for (int e = 0; e < F::E; ++e) {
-        const int m = F::out_index(tl, e);
+        int m = F::out_index(tl, e);
+        if constexpr (LOCAL) m = BlockFft<M, float>::table_index_local(m);
         pairspec[(size_t)q * M + m] = {(float)(r[e].x * scale), (float)(r[e].y * scale)};
     }
 }
@@ -218,7 +220,7 @@ k_pair_spectra(const float* __restrict__ dict, int A, int atom_lo, int atom_hi,
 // with zeros outside [0, row_len).  win may be indexed indirectly through
 // `nwin_ptr` (device-side count) so the grid can be sized for the worst case.
 // ---------------------------------------------------------------------------
-template <int M, bool STAGED = false>
+template <int M, int STAGED = 0>
 __device__ __forceinline__ void window_fft_body(const float* __restrict__ x, int row_len, int t0, int tl,
                                                 C32* sm, const C32* __restrict__ tw1, const C32* stw2,
                                                 C32* __restrict__ out) {
@@ -235,12 +237,19 @@ __device__ __forceinline__ void window_fft_body(const float* __restrict__ x, int
     __syncthreads();
     F::template pass3<-1>(r, tl, sm);
 #pragma unroll
-    for (int e = 0; e < F::E; ++e) out[STAGED ? F::bin_addr(F::out_index(tl, e)) : F::out_index(tl, e)] = r[e];
+    for (int e = 0; e < F::E; ++e) {
+        const int m = F::out_index(tl, e);
+        int at = m;
+        if constexpr (STAGED == 1) at = F::bin_addr(m);
+        if constexpr (STAGED == 2) at = F::bin_addr_local(m);
+        out[at] = r[e];
+    }
 }
 
 // STAGED: the spectrum is written in BlockFft's pass-1 shared-memory layout (SMEM_CPX entries per window, bin j at
-// bin_addr(j)) so that a consumer can bulk-copy it into its FFT buffer as it is (k_delta).
-template <int M, bool STAGED = false>
+// bin_addr(j); 2: at bin_addr_local(j), the local-first-exchange form) so that a consumer can bulk-copy it into its
+// FFT buffer as it is (k_delta).
+template <int M, int STAGED = 0>
 __global__ void __launch_bounds__(BlockFft<M, float>::T)
 k_window_fft(const float* __restrict__ src, long long row_stride, int row_len, const Win* __restrict__ win,
              const C32* __restrict__ tw1, const C32* __restrict__ tw2, C32* __restrict__ winspec,
@@ -1052,10 +1061,16 @@ struct DeltaArgs {
 constexpr int delta_elems(int m2, int want) {      // `want` values per thread if that leaves >= 32 threads and divides evenly
     return (want > 0 && m2 / (want > 0 ? want : 1) >= 32 && want % (m2 / 256) == 0) ? want : 0;
 }
+#ifndef MPB_DELTA_LOCAL
+#define MPB_DELTA_LOCAL 1      // 4096-point transforms in BlockFft's local-first-exchange form: the pass-1 -> pass-2 exchange
+                               // stays inside a half-warp (__syncwarp), one CTA barrier per transform instead of two
+#endif
 template <int M2>
 struct DeltaCfg {
     using F = BlockFft<M2, float, delta_elems(M2, MPB_DELTA_E)>;
     static constexpr int TPB = F::T < MPB_DELTA_TPB ? MPB_DELTA_TPB : F::T;
+    // the spectra tables are stored in that form's order, so producers and consumer must agree (plan build vs k_delta)
+    static constexpr bool LOCAL = MPB_DELTA_LOCAL && MPB_DELTA_SPREF && F::HAS_LOCAL && F::T == 256;
 };
 // NOPOS: the block and row tables carry no exact positions -- a candidate's "position" is the start of its block
 // (blocks order like positions, so ties resolve alike) and k_apply finds the first position of the maximum inside
@@ -1076,6 +1091,7 @@ k_delta(const DeltaArgs a) {
     float* st0 = reinterpret_cast<float*>(stw2 + 256 + (size_t)NT * F::SMEM_CPX) + (size_t)sb * 2 * a.cap;
     float* st1 = st0 + a.cap;
     constexpr bool DEFER = MPB_DELTA_DEFER && NW == 8;   // needs dedicated row warps (M2 >= 4096)
+    constexpr bool LOCAL = DeltaCfg<M2>::LOCAL;
     __shared__ float2 s_bv_static[NT * 64 * (DEFER ? 2 : 1)];
     __shared__ __align__(8) unsigned long long s_bar[3 * NT];
     float2* sBV = s_bv_static + sb * 64 * (DEFER ? 2 : 1);   // [which*32 + block] = (value, position as int bits); DEFER: x2 (item parity)
@@ -1227,7 +1243,10 @@ k_delta(const DeltaArgs a) {
                 while (!mbar_try_wait(barS, phaseS)) {}
                 phaseS ^= 1u;
 #pragma unroll
-                for (int e = 0; e < F::E; ++e) r[e] = cmul(sm[F::slot_addr(tl, e)], r[e]);
+                for (int e = 0; e < F::E; ++e) {
+                    if constexpr (LOCAL) r[e] = cmul(sm[F::slot_addr_local(tl, e)], r[e]);
+                    else r[e] = cmul(sm[F::slot_addr(tl, e)], r[e]);
+                }
             } else {
                 const C32* __restrict__ S = a.atomspec + (size_t)u.atom * M2;
 #pragma unroll
@@ -1239,12 +1258,20 @@ k_delta(const DeltaArgs a) {
                 }
             }
         }
-        if constexpr (MPB_TWGEN && F::R1 >= 4) F::template pass1_gen<1>(r, tl, sm, a.tw1);
-        else F::template pass1<1>(r, tl, sm, a.tw1);
-        __syncthreads();
-        F::template pass2<1>(r, tl, sm, stw2);
-        __syncthreads();
-        F::template pass3<1>(r, tl, sm);
+        if constexpr (LOCAL) {
+            F::template pass1_local<1>(r, tl, sm, a.tw1);
+            __syncwarp();                                // the first exchange stays inside each half-warp
+            F::template pass2_local<1>(r, tl, sm, stw2);
+            __syncthreads();
+            F::template pass3_local<1>(r, tl, sm);
+        } else {
+            if constexpr (MPB_TWGEN && F::R1 >= 4) F::template pass1_gen<1>(r, tl, sm, a.tw1);
+            else F::template pass1<1>(r, tl, sm, a.tw1);
+            __syncthreads();
+            F::template pass2<1>(r, tl, sm, stw2);
+            __syncthreads();
+            F::template pass3<1>(r, tl, sm);
+        }
 
         if (q_ok) {
             while (!mbar_try_wait(bar, phase)) {}

@@ -165,11 +165,12 @@ static int launch_window_fft_ex(int M, const C32* tw1, const C32* tw2, const flo
         using F = BlockFft<MM, float>;
         const size_t smem = (size_t)(F::SMEM_CPX + 256) * sizeof(C32);
         if (staged) {
-            MPB_CUDA((allow_smem(k_window_fft<MM, true>, smem)));
-            k_window_fft<MM, true><<<nwin, F::T, smem, st>>>(src, row_stride, row_len, win, tw1, tw2, winspec, skip);
+            constexpr int FORM = DeltaCfg<MM>::LOCAL ? 2 : 1;      // the layout k_delta<MM> reads
+            MPB_CUDA((allow_smem(k_window_fft<MM, FORM>, smem)));
+            k_window_fft<MM, FORM><<<nwin, F::T, smem, st>>>(src, row_stride, row_len, win, tw1, tw2, winspec, skip);
         } else {
-            MPB_CUDA((allow_smem(k_window_fft<MM, false>, smem)));
-            k_window_fft<MM, false><<<nwin, F::T, smem, st>>>(src, row_stride, row_len, win, tw1, tw2, winspec, skip);
+            MPB_CUDA((allow_smem(k_window_fft<MM, 0>, smem)));
+            k_window_fft<MM, 0><<<nwin, F::T, smem, st>>>(src, row_stride, row_len, win, tw1, tw2, winspec, skip);
         }
     });
     MPB_LAUNCH_CHECK("k_window_fft");
@@ -528,9 +529,10 @@ static int build_sgram_tables(Plan* p, cudaStream_t st) {
     MPB_DISPATCH_M(p->M2, {
         using F = BlockFft<MM, double>;
         const size_t smem = (size_t)(F::SMEM_CPX + 256) * sizeof(cpx<double>);
-        MPB_CUDA((allow_smem(k_pair_spectra<MM, double>, smem)));
-        k_pair_spectra<MM, double><<<p->npairs, F::T, smem, st>>>(p->dict, p->A, p->lo, p->hi, p->tw1bd, p->tw2d,
-                                                                   p->pairspec2, p->dict_skip);
+        constexpr bool LOCAL = DeltaCfg<MM>::LOCAL;                // the order k_delta<MM> loads the table in
+        MPB_CUDA((allow_smem(k_pair_spectra<MM, double, LOCAL>, smem)));
+        k_pair_spectra<MM, double, LOCAL><<<p->npairs, F::T, smem, st>>>(p->dict, p->A, p->lo, p->hi, p->tw1bd, p->tw2d,
+                                                                          p->pairspec2, p->dict_skip);
     });
     MPB_LAUNCH_CHECK("k_pair_spectra");
     return launch_window_fft_ex(p->M2, p->tw1b, p->tw2, p->dict, p->A, p->A, p->win_atoms, p->K, p->atomspec, st,
@@ -549,7 +551,7 @@ static int preload_kernels(Plan* p) {
     MPB_DISPATCH_M(p->M, {
         touch(k_apply<MM, true>);
         touch(k_apply<MM, false>);
-        touch(k_window_fft<MM, false>);
+        touch(k_window_fft<MM, 0>);
         touch(k_corr<MM, MODE_BLOCKMAX>);
         touch(k_corr<MM, MODE_DENSE>);
         touch(k_corr<MM, MODE_DENSE | MODE_BLOCKMAX>);
@@ -557,7 +559,7 @@ static int preload_kernels(Plan* p) {
         touch(k_corr<MM, MODE_DENSE | MODE_BLOCKMAX | MODE_ROWMAX>);
     });
     if (p->mode == MPB200_MODE_SGRAM) {
-        MPB_DISPATCH_M(p->M2, { touch(k_delta<MM, true>); touch(k_delta<MM, false>); touch(k_window_fft<MM, true>); });
+        MPB_DISPATCH_M(p->M2, { touch(k_delta<MM, true>); touch(k_delta<MM, false>); touch(k_window_fft<MM, 1>); touch(k_window_fft<MM, 2>); });
     }
     touch(k_gram_update<16>);
     touch(k_gram_update<32>);

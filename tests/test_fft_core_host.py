@@ -28,6 +28,9 @@ def emu(tmp_path_factory):
     lib.emu_fft.restype = C.c_int
     lib.emu_max_conflict.argtypes = [C.c_int, C.c_int]
     lib.emu_max_conflict.restype = C.c_int
+    lib.emu_fft_local.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, dp, dp]
+    lib.emu_fft_local.restype = C.c_int
+    lib.emu_max_conflict_local.restype = C.c_int
     return lib
 
 
@@ -117,3 +120,27 @@ def test_synthesised_gram_row_identity():
         if 0 <= p + l < n:
             want[p + l] = -v * gram(d0, l)              # map[t] = sum_i r[t+i] d[i], and r changed by -v d_k*[t+i-p]
     np.testing.assert_allclose(delta, want, atol=1e-9)
+
+
+@pytest.mark.parametrize("staged", [0, 1])
+@pytest.mark.parametrize("direction", [-1, 1])
+def test_local_first_exchange_form(emu, direction, staged):
+    """BlockFft<4096>::pass*_local: the exchange between pass 1 and pass 2 must stay inside a half-warp (the
+    emulation finishes pass 1 AND pass 2 of one half-warp before it touches the next), inputs are dealt in the
+    permuted table order, a staged spectrum is read from the slots pass 1 overwrites, and the result is the plain
+    DFT in natural order; every shared-memory instruction of the form is bank-conflict free."""
+    m = 4096
+    rng = np.random.default_rng(7 + direction + staged)
+    x = rng.standard_normal(m) + 1j * rng.standard_normal(m)
+    want = np.fft.fft(x) if direction < 0 else np.fft.ifft(x) * m
+    re, im = np.ascontiguousarray(x.real), np.ascontiguousarray(x.imag)
+    ore, oim, tre, tim = np.empty(m), np.empty(m), np.empty(m), np.empty(m)
+    dp = C.POINTER(C.c_double)
+    rc = emu.emu_fft_local(direction, staged, re.ctypes.data_as(dp), im.ctypes.data_as(dp), ore.ctypes.data_as(dp),
+                           oim.ctypes.data_as(dp), tre.ctypes.data_as(dp), tim.ctypes.data_as(dp))
+    assert rc == 0
+    got = ore + 1j * oim
+    assert np.linalg.norm(got - want) <= 5e-7 * np.linalg.norm(want)
+    # the permuted table is a permutation of the input (nibble swap inside each block of 256 bins)
+    assert np.array_equal(np.sort(tre), np.sort(re))
+    assert emu.emu_max_conflict_local() == 1
