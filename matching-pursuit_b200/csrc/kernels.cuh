@@ -1062,8 +1062,10 @@ constexpr int delta_elems(int m2, int want) {      // `want` values per thread i
     return (want > 0 && m2 / (want > 0 ? want : 1) >= 32 && want % (m2 / 256) == 0) ? want : 0;
 }
 #ifndef MPB_DELTA_LOCAL
-#define MPB_DELTA_LOCAL 1      // 4096-point transforms in BlockFft's local-first-exchange form: the pass-1 -> pass-2 exchange
-                               // stays inside a half-warp (__syncwarp), one CTA barrier per transform instead of two
+#define MPB_DELTA_LOCAL 0      // 1: 4096-point transforms in BlockFft's local-first-exchange form (the pass-1 -> pass-2
+                               // exchange stays inside a half-warp, __syncwarp; one CTA barrier per transform instead of
+                               // two).  Correct (parity suite green) but measured 8.78 against 8.71 ms per 256 signals:
+                               // the warps wait at the remaining barrier instead.  Kept as a measured variant.
 #endif
 template <int M2>
 struct DeltaCfg {
