@@ -325,6 +325,8 @@ __global__ void __launch_bounds__((BlockFft<M, float>::T < 256 ? 256 : BlockFft<
 k_corr(const CorrArgs a) {
     pdl_prologue();
     if (a.skip && *a.skip) return;
+    // the FFT route inside the map modes usually has no window at all (device-side count): leave before anything is set up
+    if (a.nwin_ptr && (int)blockIdx.y >= *a.nwin_ptr) return;
     using F = BlockFft<M, float>;
     constexpr int TPB = F::T < 256 ? 256 : F::T;
     constexpr int NT = TPB / F::T;   // transforms (atom pairs) per CTA
