@@ -13,7 +13,9 @@
 //     tensor-map or descriptor stride can express, so it is EXPANDED in shared memory: the signal segment is staged
 //     once per CTA, and every tap block writes H (hi and lo halves) in the canonical K-major no-swizzle core-matrix
 //     layout (8 rows x 16 bytes per core matrix).
-//   * B operand = the dictionary tile D[k, i0 + i] (K-major as stored), split into hi and lo on the way in.
+//   * B operand = the dictionary tile D[k, i0 + i]: a pre-pass (k_gemm_pack_dict) splits the dictionary into hi and
+//     lo halves and stores every (256 atoms x 32 taps) tile in the core-matrix layout, so a tile pair is ONE 64 KB bulk
+//     asynchronous copy (TMA) per tap block instead of 48 stores per thread.
 //   * one elected thread issues the 12 MMAs of the block and commits them to an mbarrier; the staging of the next
 //     block (other shared-memory stage) runs under them.
 //   * epilogue: tcgen05.ld 32 lanes x 32 columns per warp, coalesced stores (lanes = consecutive positions).
@@ -78,9 +80,40 @@ __device__ __forceinline__ void g_split(float v, float& hi, float& lo) {
     lo = v - hi;
 }
 
+// Dictionary pre-pass: packed[((kt * nkb + kb) * 2 + half) * G_D_ELEMS + core_off(r, c)] = hi / lo half of
+// d[kt*GN + r, kb*GK + c] (zero beyond K and A).  grid = (nkb, K tiles), GN threads: thread = atom row.
+__global__ void __launch_bounds__(GN)
+k_gemm_pack_dict(const float* __restrict__ dict, int K, int A, int nkb, float* __restrict__ packed) {
+    const int kb = blockIdx.x, kt = blockIdx.y, r = threadIdx.x;
+    const int k = kt * GN + r, i0 = kb * GK;
+    float* __restrict__ hi = packed + ((size_t)(kt * nkb + kb) * 2) * G_D_ELEMS;
+    float* __restrict__ lo = hi + G_D_ELEMS;
+    const float* __restrict__ dk = dict + (size_t)(k < K ? k : 0) * A;
+    const bool vec = (A & 3) == 0 && k < K;
+#pragma unroll
+    for (int c1 = 0; c1 < GK / 4; ++c1) {
+        float v[4];
+        if (vec && i0 + 4 * c1 + 3 < A) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(dk + i0 + 4 * c1));
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int i = i0 + 4 * c1 + e;
+                v[e] = (k < K && i < A) ? __ldg(dk + i) : 0.f;
+            }
+        }
+        float4 h, l;
+        g_split(v[0], h.x, l.x); g_split(v[1], h.y, l.y); g_split(v[2], h.z, l.z); g_split(v[3], h.w, l.w);
+        const int o = g_core_off(r, 4 * c1);
+        *reinterpret_cast<float4*>(hi + o) = h;
+        *reinterpret_cast<float4*>(lo + o) = l;
+    }
+}
+
 struct GemmCorrArgs {
     const float* signal;   // (B, N)
-    const float* dict;     // (K, A) used as given
+    const float* packed;   // dictionary tiles from k_gemm_pack_dict
     float* out;            // (B, K, N)
     int N, K, A;
     int spin_mma;          // > 0: peak probe -- skip staging/epilogue traffic and issue this many extra MMA blocks
@@ -90,7 +123,8 @@ __global__ void __launch_bounds__(G_THREADS, 1)
 k_corr_gemm(const GemmCorrArgs a) {
     extern __shared__ __align__(1024) unsigned char graw[];
     float* stage0 = reinterpret_cast<float*>(graw);
-    __shared__ __align__(8) unsigned long long s_done[G_STAGES];
+    __shared__ __align__(8) unsigned long long s_done[G_STAGES];     // the MMAs that read a stage have completed
+    __shared__ __align__(8) unsigned long long s_full[G_STAGES];     // a stage's dictionary tiles have landed
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int t0 = blockIdx.x * GM, k0 = blockIdx.y * GN, b = blockIdx.z;
@@ -100,7 +134,7 @@ k_corr_gemm(const GemmCorrArgs a) {
     const float* __restrict__ x = a.signal + (size_t)b * a.N;
     for (int i = tid; i < seg; i += G_THREADS) sx[i] = (t0 + i < a.N) ? x[t0 + i] : 0.f;
     if (tid == 0) {
-        for (int s = 0; s < G_STAGES; ++s) g_mbar_init(&s_done[s], 1);
+        for (int s = 0; s < G_STAGES; ++s) { g_mbar_init(&s_done[s], 1); g_mbar_init(&s_full[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -112,7 +146,8 @@ k_corr_gemm(const GemmCorrArgs a) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = s_tmem;
 
-    unsigned phase[G_STAGES] = {0, 0};
+    unsigned phase[G_STAGES] = {0, 0}, fphase[G_STAGES] = {0, 0};
+    const int nkt_y = blockIdx.y;
     const int total_blocks = nkb + (a.spin_mma > 0 ? a.spin_mma : 0);
     for (int kb = 0; kb < total_blocks; ++kb) {
         const int s = kb % G_STAGES;
@@ -123,6 +158,15 @@ k_corr_gemm(const GemmCorrArgs a) {
         if (kb >= G_STAGES) {                       // the MMAs that read this stage two blocks ago have completed
             g_mbar_wait(&s_done[s], phase[s]);
             phase[s] ^= 1u;
+        }
+        if (kb < nkb && tid == 0) {
+            // dictionary tiles (hi + lo, adjacent in the stage): one bulk copy, issued first so that it lands under the
+            // Hankel expansion below
+            const unsigned bytes = 2u * G_D_ELEMS * 4u;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(g_smem_u32(&s_full[s])), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(g_smem_u32(Dh)), "l"(a.packed + ((size_t)(nkt_y * nkb + kb) * 2) * G_D_ELEMS), "r"(bytes),
+                           "r"(g_smem_u32(&s_full[s])) : "memory");
         }
         if (kb < nkb) {
             const int i0 = kb * GK;
@@ -141,37 +185,15 @@ k_corr_gemm(const GemmCorrArgs a) {
                     *reinterpret_cast<float4*>(Hl + o) = l;
                 }
             }
-            // dictionary tile: thread = atom rows tid and tid + 128
-#pragma unroll
-            for (int half = 0; half < GN / G_THREADS; ++half) {
-                const int r = tid + half * G_THREADS, k = k0 + r;
-                const float* __restrict__ dk = a.dict + (size_t)(k < a.K ? k : 0) * a.A;
-                const bool vec = (a.A & 3) == 0 && k < a.K;               // rows are 16-byte aligned: one load per core-matrix row
-#pragma unroll
-                for (int c1 = 0; c1 < GK / 4; ++c1) {
-                    float v[4];
-                    if (vec && i0 + 4 * c1 + 3 < a.A) {
-                        const float4 q = __ldg(reinterpret_cast<const float4*>(dk + i0 + 4 * c1));
-                        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int i = i0 + 4 * c1 + e;
-                            v[e] = (k < a.K && i < a.A) ? __ldg(dk + i) : 0.f;
-                        }
-                    }
-                    float4 h, l;
-                    g_split(v[0], h.x, l.x); g_split(v[1], h.y, l.y); g_split(v[2], h.z, l.z); g_split(v[3], h.w, l.w);
-                    const int o = g_core_off(r, 4 * c1);
-                    *reinterpret_cast<float4*>(Dh + o) = h;
-                    *reinterpret_cast<float4*>(Dl + o) = l;
-                }
-            }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic writes -> visible to the tensor core
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         if (tid == 0) {
+            if (kb < nkb) {
+                g_mbar_wait(&s_full[s], fphase[s]);
+                fphase[s] ^= 1u;
+            }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t hh = g_smem_u32(Hh), hl = g_smem_u32(Hl), dh = g_smem_u32(Dh), dl = g_smem_u32(Dl);
 #pragma unroll
@@ -229,9 +251,20 @@ extern "C" int mpb200_correlate_gemm(const float* signal, int batch, int n_sampl
     if (!signal || !d || batch < 1 || n_samples < 1 || n_atoms < 1 || atom_size < 1 || (!fm_out && spin_blocks <= 0))
         return fail(MPB200_EINVAL, "bad argument");
     if (batch > 65535) return fail(MPB200_EINVAL, "batch must be <= 65535");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nkb_h = (atom_size + GK - 1) / GK, nkt = (n_atoms + GN - 1) / GN;
+    float* packed = nullptr;
+    const size_t packed_elems = (size_t)nkt * nkb_h * 2 * G_D_ELEMS;
+    cudaError_t e = cudaMallocAsync((void**)&packed, packed_elems * sizeof(float), st);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(MPB200_ENOMEM, std::string("packed dictionary: ") + cudaGetErrorString(e));
+    }
+    k_gemm_pack_dict<<<dim3(nkb_h, nkt), GN, 0, st>>>(d, n_atoms, atom_size, nkb_h, packed);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     GemmCorrArgs a;
     a.signal = signal;
-    a.dict = d;
+    a.packed = packed;
     a.out = fm_out;
     a.N = n_samples;
     a.K = n_atoms;
@@ -239,13 +272,18 @@ extern "C" int mpb200_correlate_gemm(const float* signal, int batch, int n_sampl
     a.spin_mma = spin_blocks;
     const int nkb = (atom_size + GK - 1) / GK;
     const size_t smem = (size_t)G_STAGES * G_STAGE_BYTES + (size_t)(GM + nkb * GK) * sizeof(float);
-    if (smem > 227 * 1024) return fail(MPB200_EINVAL, "atom too long for the staged signal segment of the GEMM route");
-    cudaError_t e = cudaFuncSetAttribute(k_corr_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail(MPB200_ECUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-    dim3 grid((n_samples + GM - 1) / GM, (n_atoms + GN - 1) / GN, batch);
-    k_corr_gemm<<<grid, G_THREADS, smem, (cudaStream_t)stream>>>(a);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(MPB200_ECUDA, std::string("launch k_corr_gemm: ") + cudaGetErrorString(e));
+    if (smem > 227 * 1024) {
+        cudaFreeAsync(packed, st);
+        return fail(MPB200_EINVAL, "atom too long for the staged signal segment of the GEMM route");
+    }
+    e = cudaFuncSetAttribute(k_corr_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+        dim3 grid((n_samples + GM - 1) / GM, (n_atoms + GN - 1) / GN, batch);
+        k_corr_gemm<<<grid, G_THREADS, smem, st>>>(a);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(packed, st);
+    if (e != cudaSuccess) return fail(MPB200_ECUDA, std::string("k_corr_gemm: ") + cudaGetErrorString(e));
     return MPB200_OK;
 }
