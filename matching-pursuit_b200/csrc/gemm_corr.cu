@@ -255,6 +255,10 @@ extern "C" int mpb200_correlate_gemm(const float* signal, int batch, int n_sampl
     const int nkb_h = (atom_size + GK - 1) / GK, nkt = (n_atoms + GN - 1) / GN;
     float* packed = nullptr;
     const size_t packed_elems = (size_t)nkt * nkb_h * 2 * G_D_ELEMS;
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) keep_async_pool(dev);
+    }
     cudaError_t e = cudaMallocAsync((void**)&packed, packed_elems * sizeof(float), st);
     if (e != cudaSuccess) {
         cudaGetLastError();

@@ -25,6 +25,21 @@ int fail(int code, const std::string& msg) {
     return code;
 }
 
+void keep_async_pool(int device) {
+    static std::mutex mu;
+    static bool done[64] = {false};
+    if (device < 0 || device >= 64) return;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done[device]) return;
+    done[device] = true;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+}
+
 #define MPB_CUDA(expr)                                                                          \
     do {                                                                                        \
         cudaError_t _e = (expr);                                                                \
@@ -1281,6 +1296,7 @@ static int select_dense_impl(const float* fm, int batch, int n_atoms, int n_samp
     const size_t need = (size_t)G * batch;
     cudaStream_t st = (cudaStream_t)stream;
     Best* part = nullptr;
+    keep_async_pool(dev);
     {
         cudaError_t e = cudaMallocAsync((void**)&part, need * sizeof(Best), st);
         if (e != cudaSuccess) {

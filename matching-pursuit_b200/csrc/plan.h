@@ -99,4 +99,9 @@ struct Plan {
 
 int fail(int code, const std::string& msg);
 
+// Stream-ordered scratch (cudaMallocAsync) is only cheap when the device's default memory pool keeps what is freed
+// into it: by default the pool hands everything back to the driver at the next synchronisation and every call pays a
+// driver allocation (milliseconds).  Raises the pool's release threshold once per device.
+void keep_async_pool(int device);
+
 }  // namespace mpb
