@@ -343,15 +343,18 @@ k_corr(const CorrArgs a) {
     float2* sBV = SEP ? sY + a.bm_cap : s_bv_static + sb * 64;   // [which*32 + i] = (value, position as int bits)
     for (int i = threadIdx.x; i < 256; i += TPB) stw2[i] = a.tw2[i];
 
-    int q = blockIdx.x * NT + sb;
-    const bool q_ok = q < a.npairs;
-    if (!q_ok) q = a.npairs - 1;
-    const C32* __restrict__ Eq = a.pairspec + (size_t)q * M;
     const int nwin = a.nwin_ptr ? *a.nwin_ptr : a.nwin;
     const int blk = 1 << a.blk_shift;
     const int warp = tl >> 5, lane = tl & 31;
     __syncthreads();
 
+    // A CTA keeps a pair (group) and walks the windows; launches with fewer CTAs than pair groups along x (the FFT
+    // route inside the map modes, whose window list is usually empty) walk the pair groups as well.
+    for (int qg = blockIdx.x; qg * NT < a.npairs; qg += gridDim.x) {
+    int q = qg * NT + sb;
+    const bool q_ok = q < a.npairs;
+    if (!q_ok) q = a.npairs - 1;
+    const C32* __restrict__ Eq = a.pairspec + (size_t)q * M;
     for (int w = blockIdx.y; w < nwin; w += gridDim.y) {
         const Win wi = a.win[w];
         const C32* __restrict__ X = a.winspec + (size_t)w * M;
@@ -496,6 +499,7 @@ k_corr(const CorrArgs a) {
             }
         }
         if constexpr (!SEP) __syncthreads();  // buffer free for the next window
+    }
     }
 }
 

@@ -198,7 +198,7 @@ static int launch_window_fft(Plan* p, const float* src, long long row_stride, in
 }
 
 template <int MODE>
-static int launch_corr(Plan* p, CorrArgs a, int groups, cudaStream_t st, bool pdl = false) {
+static int launch_corr(Plan* p, CorrArgs a, int groups, cudaStream_t st, bool pdl = false, int max_gx = 0) {
     if (a.nwin <= 0) return MPB200_OK;
     a.bm_cap = p->bm_cap;
     MPB_DISPATCH_M(p->M, {
@@ -209,6 +209,7 @@ static int launch_corr(Plan* p, CorrArgs a, int groups, cudaStream_t st, bool pd
         if (MPB_CORR_SEP && (MODE & MODE_ROWMAX) != 0) smem += (size_t)NT * (p->bm_cap + 64) * sizeof(float2);
         MPB_CUDA(allow_smem(k_corr<MM, MODE>, smem));
         dim3 grid((a.npairs + NT - 1) / NT, groups);
+        if (max_gx > 0 && (int)grid.x > max_gx) grid.x = max_gx;      // the CTAs walk the remaining pair groups
         if (pdl) MPB_CUDA(launch_pdl(k_corr<MM, MODE>, grid, dim3(TPB), smem, st, a));
         else k_corr<MM, MODE><<<grid, TPB, smem, st>>>(a);
     });
@@ -230,7 +231,8 @@ static int corr_groups(const Plan* p, int nwin) {
 // at all, so the launch is kept just deep enough to fill the chip twice instead of eight times.
 static int trunc_groups(const Plan* p, int nwin) {
     const int tpb_pairs = (p->M >= 4096) ? 1 : (4096 / p->M > 8 ? 8 : 4096 / p->M);
-    const int gx = (p->npairs + tpb_pairs - 1) / tpb_pairs;
+    int gx = (p->npairs + tpb_pairs - 1) / tpb_pairs;
+    if (gx > p->sm_count) gx = p->sm_count;           // launch_corr caps the x extent there for this route
     int g = (p->sm_count * 2 + gx - 1) / gx;
     if (g < 1) g = 1;
     if (g > nwin) g = nwin;
@@ -452,7 +454,7 @@ static int step_refresh_raw(Plan* p, int batch, cudaStream_t st) {
             a.dense_atom_stride = p->NS;
             a.dense_col_off = 0;
             a.pos_free = p->pos_free ? 1 : 0;
-            rc = launch_corr<MODE_DENSE | MODE_BLOCKMAX | MODE_ROWMAX>(p, a, trunc_groups(p, batch), st, true);
+            rc = launch_corr<MODE_DENSE | MODE_BLOCKMAX | MODE_ROWMAX>(p, a, trunc_groups(p, batch), st, true, p->sm_count);
         }
     } else if (p->mode == MPB200_MODE_GRAM) {
         const bool refresh = p->refresh_every > 0 && (p->iter + 1) % (unsigned)p->refresh_every == 0;
@@ -493,7 +495,7 @@ static int step_refresh_raw(Plan* p, int batch, cudaStream_t st) {
             a.dense_row_stride = (long long)p->nloc * p->N;
             a.dense_atom_stride = p->N;
             a.dense_col_off = 0;
-            rc = launch_corr<MODE_DENSE | MODE_BLOCKMAX | MODE_ROWMAX>(p, a, trunc_groups(p, batch), st, true);
+            rc = launch_corr<MODE_DENSE | MODE_BLOCKMAX | MODE_ROWMAX>(p, a, trunc_groups(p, batch), st, true, p->sm_count);
         }
     } else {
         CorrArgs a = base_corr_args(p);
