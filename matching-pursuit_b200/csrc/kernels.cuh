@@ -398,6 +398,53 @@ k_corr(const CorrArgs a) {
             }
             __syncthreads();
             const bool second = 2 * q + 1 < a.nloc;
+            if constexpr (MPB_CORR_LEAN && M == 512) {
+                // blocks of 16 positions, one warp per transform: TWO blocks per step (lanes 0-15 / 16-31, segmented
+                // redux.sync on an order-preserving key for the value, equality + redux.sync.min for its first
+                // position); lane l collects block l and the table is written coalesced at the end.  The generic
+                // path below spends a 5-step shuffle tree per block and one lane's scattered stores -- at this block
+                // size that was four times the transform itself (the first pass of a configs[3] band).
+                const unsigned seg = lane < 16 ? 0x0000ffffu : 0xffff0000u;
+                const int valid = min(limit, wi.nvb * 16);
+                float keep_va = -INFINITY, keep_vb = -INFINITY;
+                int keep_ia = INT_MAX, keep_ib = INT_MAX;
+                for (int i2 = 0; i2 < wi.nvb; i2 += 2) {
+                    const int m = i2 * 16 + lane;
+                    const bool in = m < valid;
+                    const float2 c = in ? sY[m] : make_float2(-INFINITY, -INFINITY);
+                    const int ka = __reduce_max_sync(seg, float_key(c.x));
+                    const int kb = __reduce_max_sync(seg, float_key(c.y));
+                    float va = __int_as_float(ka ^ ((ka >> 31) & 0x7fffffff));
+                    float vb = __int_as_float(kb ^ ((kb >> 31) & 0x7fffffff));
+                    if (!(va == va)) va = -INFINITY;              // a NaN never wins
+                    if (!(vb == vb)) vb = -INFINITY;
+                    const int ia = __reduce_min_sync(seg, (in && c.x + 0.0f == va) ? m : INT_MAX);
+                    const int ib = __reduce_min_sync(seg, (in && c.y + 0.0f == vb) ? m : INT_MAX);
+                    // lanes i2 and i2 + 1 take the results of the lower / upper half-warp
+                    const int src = (lane == i2 + 1) ? 16 : 0;
+                    const float sva = __shfl_sync(0xffffffffu, va, src), svb = __shfl_sync(0xffffffffu, vb, src);
+                    const int sia = __shfl_sync(0xffffffffu, ia, src), sib = __shfl_sync(0xffffffffu, ib, src);
+                    if (lane == i2 || lane == i2 + 1) {
+                        keep_va = sva; keep_vb = svb;
+                        keep_ia = sia; keep_ib = sib;
+                    }
+                }
+                if (lane < wi.nvb && q_ok) {
+                    const int pa = (keep_ia == INT_MAX) ? INT_MAX : wi.t0 + keep_ia;
+                    const int pb = (keep_ib == INT_MAX) ? INT_MAX : wi.t0 + keep_ib;
+                    const size_t o = ((size_t)wi.row * a.nloc + 2 * q) * a.NB + wi.blk0 + lane;
+                    a.bm_val[o] = keep_va;
+                    a.bm_pos[o] = pa;
+                    if (second) {
+                        a.bm_val[o + a.NB] = keep_vb;
+                        a.bm_pos[o + a.NB] = pb;
+                    }
+                    if constexpr ((MODE & MODE_ROWMAX) != 0) {
+                        sBV[lane] = make_float2(keep_va, __int_as_float(pa));
+                        sBV[32 + lane] = make_float2(keep_vb, __int_as_float(pb));
+                    }
+                }
+            } else
             for (int i = warp; i < wi.nvb; i += NW) {
                 const int hi = min((i + 1) * blk, limit);
                 float va = -INFINITY, vb = -INFINITY;
