@@ -49,6 +49,21 @@ __device__ __forceinline__ cpx<float> operator-(cpx<float> a, cpx<float> b) {
 template <typename T> MPB_HD cpx<T> cmul(cpx<T> a, cpx<T> b) {
     return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
 }
+#ifndef MPB_CMUL2
+#define MPB_CMUL2 1   // complex multiply as TWO packed instructions: FMUL2 a.F32x2 * b.x ; FFMA2 -a.F32x2.LO_HI.NP * b.y + t
+                      // (the swap and the per-half negation of the first operand are operand modifiers of FFMA2, the scalar
+                      // factors are broadcast operands or immediates)
+#endif
+#if MPB_F32X2 && MPB_CMUL2 && defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+__device__ __forceinline__ cpx<float> cmul(cpx<float> a, cpx<float> b) {
+    const float2 t = __fmul2_rn(make_float2(a.x, a.y), make_float2(b.x, b.x));
+    const float2 r = __ffma2_rn(make_float2(-a.y, a.x), make_float2(b.y, b.y), t);
+    return {r.x, r.y};
+}
+#define MPB_CMUL2_ACTIVE 1
+#else
+#define MPB_CMUL2_ACTIVE 0
+#endif
 template <typename T> MPB_HD cpx<T> cconj(cpx<T> a) { return {a.x, -a.y}; }
 
 template <int B, int E, typename F>
@@ -87,6 +102,14 @@ MPB_HD cpx<T> tw_const(cpx<T> v) {
     } else if constexpr (q == 24) {          // * (-DIR * i)
         if constexpr (DIR > 0) return {v.y, -v.x};
         else return {-v.y, v.x};
+    } else if constexpr (MPB_CMUL2_ACTIVE && std::is_same<T, float>::value) {
+        // the whole rotation as one two-instruction complex multiply by the constant exp(DIR * 2 pi i q / 32)
+        constexpr int quad = q / 8, r = q % 8;
+        constexpr T c = (T)Cos32<r>::value, s = (T)Cos32<8 - r>::value;
+        constexpr T wr = quad == 0 ? c : quad == 1 ? -s : quad == 2 ? -c : s;
+        constexpr T wi0 = quad == 0 ? s : quad == 1 ? c : quad == 2 ? -s : -c;
+        constexpr T wi = DIR > 0 ? wi0 : -wi0;
+        return cmul(v, cpx<T>{wr, wi});
     } else {
         // reduce to first quadrant: angle = quad*8 + r, r in 1..7
         constexpr int quad = q / 8, r = q % 8;
@@ -309,6 +332,31 @@ struct BlockFft {
                     v = cmul(v, w);
                 }
                 sm[addr(m1, m2, j3)] = v;
+            });
+        });
+    }
+
+    // pass 2 with the twiddles w_256^(j3*m2) generated from z = w_256^j3 (j3 = tl & 15 never changes, so the caller
+    // keeps z in two registers): 14 two-instruction multiplications instead of 15 shared-memory loads per butterfly --
+    // the shared-memory data pipe, not the issue slots, is what k_delta runs out of.
+    template <int DIR>
+    static MPB_HD void pass2_gen(C* r, int tl, C* sm, C z) {
+        if constexpr (DIR < 0) z.y = -z.y;
+        static_for<0, NB2>([&](auto uc) {
+            constexpr int u = decltype(uc)::value;
+            const int beta = tl + T * u;
+            const int j3 = beta & 15, m1 = beta >> 4;
+            static_for<0, 16>([&](auto xc) {
+                constexpr int x = decltype(xc)::value;
+                r[u * 16 + x] = sm[addr(m1, x, j3)];
+            });
+            Dft<16, DIR, Real>::run(r + u * 16);
+            C zp[16];
+            powers<16>(z, zp);
+            sm[addr(m1, 0, j3)] = r[u * 16];
+            static_for<1, 16>([&](auto m2c) {
+                constexpr int m2 = decltype(m2c)::value;
+                sm[addr(m1, m2, j3)] = cmul(r[u * 16 + m2], zp[m2]);
             });
         });
     }
