@@ -82,7 +82,7 @@ def parse_args():
 # --------------------------------------------------------------------------
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw,clocks.mem")
 
     def __init__(self, index: int):
         self.index, self.samples, self.proc = index, [], None
@@ -111,7 +111,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, watts, mem = [], None, set(), [], []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for p in self.samples:
             try:
@@ -122,9 +122,17 @@ class ClockSampler:
             for name, flag in zip(names, p[2:6]):
                 if flag.lower().startswith("active"):
                     reasons.add(name)
+            try:                                       # board power and memory clock beside the SM clock: the headline
+                watts.append(float(p[6]))              # kernel runs at the board's power cap
+                mem.append(float(p[7]))
+            except (ValueError, IndexError):
+                pass
         sm.sort()
+        watts.sort()
+        mem.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w": watts[len(watts) // 2] if watts else None,
+                "mem_mhz": mem[len(mem) // 2] if mem else None}
 
 
 # --------------------------------------------------------------------------

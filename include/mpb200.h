@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MPB200_VERSION 120   /* 1.2: exchange_disconnect, options FORCE_TABLES / MAX_STEPS, staged SGRAM spectra */
+#define MPB200_VERSION 130   /* 1.3: option FUSED_LOOP (one cooperative launch per pursuit in the windowed re-correlation mode) */
 
 #define MPB200_OK 0
 #define MPB200_EINVAL (-1)   /* bad argument / unsupported shape */
@@ -109,6 +109,12 @@ int mpb200_plan_info_get(mpb200_plan_t plan, mpb200_plan_info* info);
  * normalised values in the winner's +-A window (+-4 columns) are recomputed from the resident map and a second
  * block/row-max hierarchy is refreshed.  Allocates that hierarchy on first use. */
 #define MPB200_OPT_LOCAL_CONTRAST_NORM 5
+/* MPB200_OPT_FUSED_LOOP (windowed re-correlation mode, un-sharded plans): 1 (default) = mpb200_sparse_code runs the
+ * whole iteration loop of a resident batch as ONE cooperative launch (pair spectra in registers, one grid barrier
+ * per iteration) whenever one CTA per (atom-pair group, signal) fits on the device at once -- the latency-bound
+ * shapes, e.g. BASELINE configs[0]; 0 = always the stream-ordered loop of two launches per iteration.  Both give
+ * the same events bit for bit (reference loop: modules/matchingpursuit.py:298-328). */
+#define MPB200_OPT_FUSED_LOOP 6
 int mpb200_plan_set_option(mpb200_plan_t plan, int option, long long value);
 
 /* Per-kernel device timing of the pursuit loop (bench / profiling aid, no

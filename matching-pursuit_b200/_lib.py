@@ -16,9 +16,9 @@ CSRC = os.path.join(HERE, "csrc")
 # MPB200_LIBRARY points the binding at an alternative build of the same sources (A/B timing of kernel variants)
 LIB_PATH = os.environ.get("MPB200_LIBRARY") or os.path.join(HERE, "libmpb200.so")
 SOURCES = ["mpb200.cu", "fftconv.cu", "gemm_corr.cu"]
-HEADERS = ["kernels.cuh", "fft_core.cuh", "bigfft.cuh", "types.h", "plan.h"]
+HEADERS = ["kernels.cuh", "fused_loop.cuh", "fft_core.cuh", "bigfft.cuh", "types.h", "plan.h"]
 
-ABI_VERSION = 120    # MPB200_VERSION of include/mpb200.h this binding was written against
+ABI_VERSION = 130    # MPB200_VERSION of include/mpb200.h this binding was written against
 MODE_AUTO, MODE_RECORRELATE, MODE_GRAM, MODE_FULL, MODE_SGRAM = 0, 1, 2, 3, 4
 MODES = {"auto": MODE_AUTO, "recorrelate": MODE_RECORRELATE, "gram": MODE_GRAM, "full": MODE_FULL,
          "sgram": MODE_SGRAM}
@@ -49,6 +49,7 @@ def needs_build() -> bool:
         return True
     built = os.path.getmtime(LIB_PATH)
     deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(os.path.dirname(HERE), "include", "mpb200.h")]
+    deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]   # any header added later
     return any(os.path.getmtime(d) > built for d in deps if os.path.exists(d))
 
 

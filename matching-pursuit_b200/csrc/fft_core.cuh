@@ -336,31 +336,6 @@ struct BlockFft {
         });
     }
 
-    // pass 2 with the twiddles w_256^(j3*m2) generated from z = w_256^j3 (j3 = tl & 15 never changes, so the caller
-    // keeps z in two registers): 14 two-instruction multiplications instead of 15 shared-memory loads per butterfly --
-    // the shared-memory data pipe, not the issue slots, is what k_delta runs out of.
-    template <int DIR>
-    static MPB_HD void pass2_gen(C* r, int tl, C* sm, C z) {
-        if constexpr (DIR < 0) z.y = -z.y;
-        static_for<0, NB2>([&](auto uc) {
-            constexpr int u = decltype(uc)::value;
-            const int beta = tl + T * u;
-            const int j3 = beta & 15, m1 = beta >> 4;
-            static_for<0, 16>([&](auto xc) {
-                constexpr int x = decltype(xc)::value;
-                r[u * 16 + x] = sm[addr(m1, x, j3)];
-            });
-            Dft<16, DIR, Real>::run(r + u * 16);
-            C zp[16];
-            powers<16>(z, zp);
-            sm[addr(m1, 0, j3)] = r[u * 16];
-            static_for<1, 16>([&](auto m2c) {
-                constexpr int m2 = decltype(m2c)::value;
-                sm[addr(m1, m2, j3)] = cmul(r[u * 16 + m2], zp[m2]);
-            });
-        });
-    }
-
     // ------------------------------------------------------------------------------------------------------------
     // "Local first exchange" form (M = 4096, 256 threads x 16 values): the inputs are dealt to the threads so that the
     // exchange between pass 1 and pass 2 stays inside a HALF-WARP -- 16 consecutive lanes trade 16 x 16 values through

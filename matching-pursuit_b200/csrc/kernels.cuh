@@ -1111,33 +1111,11 @@ struct DeltaArgs {
                                // block/row maxima of the current item are reduced; the product phase then reads it from
                                // shared memory instead of L2
 #endif
-#ifndef MPB_DELTA_EQPRE
-#define MPB_DELTA_EQPRE 0      // 1: the NEXT item's pair spectrum (and its update record) is requested into the dead FFT
-                               // registers right after the third barrier, so that its L2 latency runs under the block
-                               // reduction.  Measured: ptxas spills 23 registers around the loop at the 80-register
-                               // budget of 3 CTAs/SM and the launch takes 10.7 instead of 8.7 ms per 256 signals.
-                               // 2: only the update record is fetched one item ahead.
-#endif
 #ifndef MPB_DELTA_FREDUX
 #define MPB_DELTA_FREDUX 1     // block maxima with redux.sync.max.f32 (CREDUX.MAX.F32, sm_100a) instead of an integer key
 #endif
 #ifndef MPB_DELTA_TRIMST
 #define MPB_DELTA_TRIMST 1     // only the updated range of the staged rows is stored back (16-byte granules)
-#endif
-#ifndef MPB_DELTA_DIRECT
-#define MPB_DELTA_DIRECT 0     // regular items (power-of-two atom, window away from the left edge, whole blocks inside the
-                               // signal): the updated values go from the registers straight to the map (no staged write,
-                               // no bulk store), the block maxima are reduced from the registers (redux.sync.max.f32) and
-                               // the NEXT item's window is requested right after the third barrier -- the store drain and
-                               // the staged block reduction no longer sit between two windows of a CTA
-#endif
-#ifndef MPB_DELTA_EQKEEP
-#define MPB_DELTA_EQKEEP 0     // 1 (with MPB_DELTA_MINB=2: 128 registers): the pair spectrum stays in registers for the run
-                               // of items that share it (a CTA walks the whole batch per pair group) instead of being
-                               // re-read from L2 for every item
-#endif
-#ifndef MPB_DELTA_TW2GEN
-#define MPB_DELTA_TW2GEN 1     // pass-2 twiddles generated in registers from one per-thread constant (no table loads)
 #endif
 #ifndef MPB_DELTA_E
 #define MPB_DELTA_E 0          // complex values per thread of k_delta's transform (0: BlockFft's default, 16 up to 4096 points)
@@ -1179,12 +1157,8 @@ k_delta(const DeltaArgs a) {
     C32* sm = stw2 + 256 + (size_t)sb * F::SMEM_CPX;
     float* st0 = reinterpret_cast<float*>(stw2 + 256 + (size_t)NT * F::SMEM_CPX) + (size_t)sb * 2 * a.cap;
     float* st1 = st0 + a.cap;
+    constexpr bool DEFER = MPB_DELTA_DEFER && NW == 8;   // needs dedicated row warps (M2 >= 4096)
     constexpr bool LOCAL = DeltaCfg<M2>::LOCAL;
-    constexpr bool DIRECT = MPB_DELTA_DIRECT && NOPOS && MPB_DELTA_SPREF && !LOCAL && F::NB2 == 1 && F::T >= 32;
-    constexpr bool DEFER = MPB_DELTA_DEFER && NW == 8 && !DIRECT;   // needs dedicated row warps (M2 >= 4096)
-    constexpr int PSTR = 20;                             // DIRECT: per-(warp, row) stride of the partial block maxima (<= 17 blocks)
-    __shared__ float s_part_static[DIRECT ? NT * NW * 2 * PSTR : 1];
-    float* part = s_part_static + (DIRECT ? sb * NW * 2 * PSTR : 0);
     __shared__ float2 s_bv_static[NT * 64 * (DEFER ? 2 : 1)];
     __shared__ __align__(8) unsigned long long s_bar[3 * NT];
     float2* sBV = s_bv_static + sb * 64 * (DEFER ? 2 : 1);   // [which*32 + block] = (value, position as int bits); DEFER: x2 (item parity)
@@ -1204,7 +1178,6 @@ k_delta(const DeltaArgs a) {
     const int warp = tl >> 5, lane = tl & 31;
     const int which0 = warp - RW0;                       // row (0/1) this warp re-derives; outside [0, 2): none
     unsigned phase = 0;
-    const C32 z2 = a.tw2[16 + (tl & 15)];                // w_256^j3: root of this thread's pass-2 twiddles (TW2GEN)
     pdl_prologue();                                      // the table above is constant; everything below is not
     __syncthreads();
 
@@ -1219,7 +1192,6 @@ k_delta(const DeltaArgs a) {
         b = (int)(it0 - (long long)g * a.batch);
     }
     C32 r[F::E];
-    C32 eqr[MPB_DELTA_EQKEEP ? F::E : 1];                // EQKEEP: the pair spectrum of pair eq_q
     unsigned phaseS = 0;
     // tl == 0: request signal bb's winner spectrum into this transform's (idle) FFT buffer
     auto request_spectrum = [&](int bb) {
@@ -1237,16 +1209,17 @@ k_delta(const DeltaArgs a) {
     unsigned phaseF = 0;
     bool phaseF_armed = false;                           // a block reduction has been run (barF has a phase to wait for)
     // Row maxima of the (row, which) pair from the refreshed block maxima in `bv` and the row's previous maximum.
-    // row_phase_core: lane < rnvb holds the refreshed (value, position) of block rblk0 + lane
-    auto row_phase_core = [&](int row0, int which, int rblk0, int rnvb, float v, int at, float oldv, int oldp) {
+    auto row_phase = [&](int row0, int which, int rblk0, int rnvb, const float2* bv, float oldv, int oldp) {
         const size_t rowi = (size_t)row0 + which;
         const size_t o = rowi * a.NB;
+        float v = -INFINITY;
+        int at = INT_MAX;
         if (lane < rnvb) {
+            const float2 c = bv[which * 32 + lane];
+            v = c.x;
+            at = __float_as_int(c.y);
             a.bm_val[o + rblk0 + lane] = v;              // coalesced publication of the refreshed blocks
             if constexpr (!NOPOS) a.bm_pos[o + rblk0 + lane] = at;
-        } else {
-            v = -INFINITY;
-            at = INT_MAX;
         }
         const int old_b = oldp >> a.blk_shift;
         const bool old_ok = old_b < rblk0 || old_b >= rblk0 + rnvb;
@@ -1261,49 +1234,11 @@ k_delta(const DeltaArgs a) {
             a.row_pos[rowi] = (at == INT_MAX) ? 0 : at;
         }
     };
-    auto row_phase = [&](int row0, int which, int rblk0, int rnvb, const float2* bv, float oldv, int oldp) {
-        float v = -INFINITY;
-        int at = INT_MAX;
-        if (lane < rnvb) {
-            const float2 c = bv[which * 32 + lane];
-            v = c.x;
-            at = __float_as_int(c.y);
-        }
-        row_phase_core(row0, which, rblk0, rnvb, v, at, oldv, oldp);
-    };
-    // tl == 0: request the map window of item (pair qq, signal bb, winner position pos) into the staging rows
-    auto request_window_for = [&](int qq, int bb, int pos) {
-        const int wfirst = max(0, pos - a.A + 1), wlast = pos + a.A - 1;
-        const int wblk0 = wfirst >> a.blk_shift, wnvb = (wlast >> a.blk_shift) - wblk0 + 1;
-        const int wstart = wblk0 << a.blk_shift;
-        const unsigned bytes = (unsigned)min(wnvb << a.blk_shift, a.NS - wstart) * 4u;
-        const float* w0 = a.map + ((size_t)bb * a.nloc + 2 * qq) * a.NS + wstart;
-        const bool wsecond = 2 * qq + 1 < a.nloc;
-        bulk_wait_read0();                               // bulk stores of an earlier item have left the staging rows
-        mbar_expect_tx(bar, wsecond ? 2u * bytes : bytes);
-        bulk_load(st0, w0, bytes, bar);
-        if (wsecond) bulk_load(st1, w0 + a.NS, bytes, bar);
-    };
-    bool win_pre = false;                                // DIRECT, tl == 0: this item's window was requested by the previous item
-    constexpr bool EQPRE = MPB_DELTA_EQPRE == 1 && MPB_DELTA_SPREF;
-    constexpr bool UPRE = MPB_DELTA_EQPRE >= 1 && MPB_DELTA_SPREF;
-    int eq_q = -1;                                       // EQPRE: the pair whose spectrum r[] holds
-    GramUpdate u_nx = GramUpdate{};
-    if (UPRE && n_items > 0) u_nx = a.upd[b];
-    auto load_pair_spectrum = [&](int qq) {
-        const C32* __restrict__ Eq = a.pairspec2 + (size_t)qq * M2;
-#pragma unroll
-        for (int e = 0; e < F::E; ++e) {
-            const float2 y = __ldg(reinterpret_cast<const float2*>(Eq + F::in_index(tl, e)));
-            r[e] = C32{y.x, y.y};
-        }
-    };
     for (; n_items > 0; --n_items, b = (b + 1 == a.batch ? 0 : b + 1), g += (b == 0)) {
-        const GramUpdate u = UPRE ? u_nx : a.upd[b];
+        const GramUpdate u = a.upd[b];
         const int b_next = (b + 1 == a.batch ? 0 : b + 1);
         if (!u.valid) {                                  // CTA-uniform: this signal takes the FFT route
             if (MPB_DELTA_SPREF && tl == 0 && n_items > 1) request_spectrum(b_next);   // nobody touches the buffer now
-            if (UPRE && n_items > 1) u_nx = a.upd[b_next];
             continue;
         }
         int q = g * NT + sb;
@@ -1336,10 +1271,7 @@ k_delta(const DeltaArgs a) {
                 }
                 if (q_ok) request_window();
             }
-        } else if (tl == 0) {
-            if (q_ok && !win_pre) request_window();
-            win_pre = false;
-        }
+        } else if (tl == 0 && q_ok) request_window();
         // the old row maxima are fetched now so that the row phase never waits on memory (DEFER: those of the
         // PREVIOUS item, whose row phase runs during this one)
         float old_v[NROW];
@@ -1370,31 +1302,16 @@ k_delta(const DeltaArgs a) {
                 // the pair spectrum comes from L2 while the winner spectrum -- requested during the previous item's
                 // reduction phase -- is read from this thread's own slots of the FFT buffer (the slots pass 1
                 // overwrites below: no barrier needed)
-                if constexpr (MPB_DELTA_EQKEEP) {
-                    if (eq_q != q) {
 #pragma unroll
-                        for (int e = 0; e < F::E; ++e) {
-                            const float2 y = __ldg(reinterpret_cast<const float2*>(Eq + F::in_index(tl, e)));
-                            eqr[e] = C32{y.x, y.y};
-                        }
-                        eq_q = q;
-                    }
-                } else if constexpr (EQPRE) {
-                    if (eq_q != q) load_pair_spectrum(q);        // first item of the CTA, or after a skipped one
-                    eq_q = -1;                                   // r[] is consumed below
-                } else {
-#pragma unroll
-                    for (int e = 0; e < F::E; ++e) {
-                        const float2 y = __ldg(reinterpret_cast<const float2*>(Eq + F::in_index(tl, e)));
-                        r[e] = C32{y.x, y.y};
-                    }
+                for (int e = 0; e < F::E; ++e) {
+                    const float2 y = __ldg(reinterpret_cast<const float2*>(Eq + F::in_index(tl, e)));
+                    r[e] = C32{y.x, y.y};
                 }
                 while (!mbar_try_wait(barS, phaseS)) {}
                 phaseS ^= 1u;
 #pragma unroll
                 for (int e = 0; e < F::E; ++e) {
-                    if constexpr (MPB_DELTA_EQKEEP) r[e] = cmul(sm[F::slot_addr(tl, e)], eqr[e]);
-                    else if constexpr (LOCAL) r[e] = cmul(sm[F::slot_addr_local(tl, e)], r[e]);
+                    if constexpr (LOCAL) r[e] = cmul(sm[F::slot_addr_local(tl, e)], r[e]);
                     else r[e] = cmul(sm[F::slot_addr(tl, e)], r[e]);
                 }
             } else {
@@ -1418,68 +1335,12 @@ k_delta(const DeltaArgs a) {
             if constexpr (MPB_TWGEN && F::R1 >= 4) F::template pass1_gen<1>(r, tl, sm, a.tw1);
             else F::template pass1<1>(r, tl, sm, a.tw1);
             __syncthreads();
-            if constexpr (MPB_DELTA_TW2GEN) F::template pass2_gen<1>(r, tl, sm, z2);
-            else F::template pass2<1>(r, tl, sm, stw2);
-#ifdef MPB_EXP_NOBAR2
-            __syncwarp();
-#else
+            F::template pass2<1>(r, tl, sm, stw2);
             __syncthreads();
-#endif
             F::template pass3<1>(r, tl, sm);
         }
 
-        // DIRECT: a regular item has all 2A-1 outputs inside [0, N), whole staged blocks and one block per register slot
-        const bool regular = DIRECT && (p - (a.A - 1) - start) >= 0 && 2 * a.A == M2 && blk == F::T &&
-                             start + (nvb << a.blk_shift) <= a.N;
-        if (q_ok && regular) {
-            while (!mbar_try_wait(bar, phase)) {}
-            phase ^= 1u;
-            // Slot e of thread tl is staged index i = tl + off + blk*e, i.e. block e (+1 for the threads with
-            // tl + off >= blk: `cross`).  Together with ONE more staged element per thread and row -- slot "-1" for the
-            // crossing threads, slot "16" for the others: the unchanged head and tail of the staged blocks -- the 256
-            // threads hold every element of blocks 0..nvb-1, so block k's maximum is one redux per warp over
-            // v_k = cross ? y[k-1] : y[k] and a maximum over the warps' partial results in the row phase.
-            const int off = p - (a.A - 1) - start;
-            const int i0 = tl + off;
-            const bool cross = i0 >= blk;
-            const int je = cross ? i0 - blk : i0 + 16 * blk;
-            const bool ext_ok = cross || nvb > 16;
-            const float ext0 = ext_ok ? st0[je] : -INFINITY, ext1 = ext_ok ? st1[je] : -INFINITY;
-            float prev0 = ext0, prev1 = ext1, mine0 = -INFINITY, mine1 = -INFINITY;
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                const int i = i0 + F::T * e;
-                const float s0 = st0[i], s1 = st1[i];
-                float2 x = __ffma2_rn(make_float2(nv, nv), make_float2(r[e].x, r[e].y), make_float2(s0, s1));
-                if (e == 15 && tl == F::T - 1) {
-                    x = make_float2(s0, s1);             // output M2-1 is void: the staged value stands
-                } else {
-#ifndef MPB_EXP_NOSTG
-                    m0[i] = x.x;
-                    if (second) m1[i] = x.y;
-#endif
-                }
-#ifdef MPB_EXP_NOREDUX
-                const float m0k = (cross ? prev0 : x.x);
-                const float m1k = (cross ? prev1 : x.y);
-#else
-                const float m0k = redux_max_f32(cross ? prev0 : x.x);
-                const float m1k = redux_max_f32(cross ? prev1 : x.y);
-#endif
-                if (lane == e) { mine0 = m0k; mine1 = m1k; }
-                prev0 = x.x;
-                prev1 = x.y;
-            }
-            {
-                const float m0k = redux_max_f32(cross ? prev0 : ext0);
-                const float m1k = redux_max_f32(cross ? prev1 : ext1);
-                if (lane == 16) { mine0 = m0k; mine1 = m1k; }
-            }
-            if (lane < 17) {
-                part[(warp * 2 + 0) * PSTR + lane] = mine0;
-                part[(warp * 2 + 1) * PSTR + lane] = mine1;
-            }
-        } else if (q_ok) {
+        if (q_ok) {
             while (!mbar_try_wait(bar, phase)) {}
             phase ^= 1u;
             // output m is lag m - (A-1), i.e. position t = p - (A-1) + m, staged at index i = m + off.
@@ -1532,41 +1393,7 @@ k_delta(const DeltaArgs a) {
         fence_proxy_async();                             // generic-proxy writes -> visible to the bulk stores; the FFT
                                                          // buffer's generic writes are ordered before its bulk refill
         __syncthreads();                                 // rows updated; FFT buffer free
-        if (regular) {
-            // nothing of this item is left in the staging rows or the FFT buffer: the next item's winner spectrum AND map
-            // window are requested now, a whole reduction phase + transform ahead of their use
-            if (tl == 0 && n_items > 1) {
-                const GramUpdate un = a.upd[b_next];
-                if (un.valid) {
-                    mbar_expect_tx(barS, SBYTES);
-                    bulk_load(sm, a.atomspec + (size_t)un.atom * F::SMEM_CPX, SBYTES, barS);
-                    const int qn = (g + (b_next == 0 ? 1 : 0)) * NT + sb;
-                    if (qn < a.npairs) {
-                        request_window_for(qn, b_next, un.position);
-                        win_pre = true;
-                    }
-                }
-            }
-#pragma unroll
-            for (int wi = 0; wi < NROW; ++wi) {
-                const int which = which0 + wi;
-                if (!q_ok || which < 0 || which > 1 || (which == 1 && !second)) continue;
-                float v = -INFINITY;
-                if (lane < nvb) {
-#pragma unroll
-                    for (int w = 0; w < NW; ++w) v = fmaxf(v, part[(w * 2 + which) * PSTR + lane]);
-                    v += 0.0f;                           // -0 folds into +0
-                }
-                row_phase_core((int)((size_t)b * a.nloc + 2 * q), which, blk0, nvb, v, start + (lane << a.blk_shift),
-                               old_v[wi], old_p[wi]);
-            }
-            continue;
-        }
-#ifdef MPB_EXP_NOSTORE
-        if (false) {
-#else
         if (tl == 0 && q_ok) {
-#endif
             if constexpr (MPB_DELTA_TRIMST) {
                 // only the updated range [lo_i, hi_i) goes back, widened to 16-byte granules (the rest of the staged
                 // blocks is unchanged and only needed by the block reduction)
@@ -1583,29 +1410,13 @@ k_delta(const DeltaArgs a) {
             bulk_commit();
         }
         if (MPB_DELTA_SPREF && tl == 0 && n_items > 1) request_spectrum(b_next);
-        if constexpr (UPRE) {
-            if (n_items > 1) u_nx = a.upd[b_next];       // lands behind the block reduction
-        }
-        if constexpr (EQPRE) {
-            if (n_items > 1) {
-                // the FFT registers are dead until the next item's product: its pair spectrum is requested now
-                int qn = (g + (b_next == 0 ? 1 : 0)) * NT + sb;
-                if (qn >= a.npairs) qn = a.npairs - 1;
-                load_pair_spectrum(qn);
-                eq_q = qn;
-            }
-        }
         if constexpr (DEFER) {
             // the previous item's row maxima: its block maxima were staged before this item's barriers
             if (pv_row >= 0 && which0 >= 0 && which0 < 2 && (which0 == 0 || (pv_win & 1)))
                 row_phase(pv_row, which0, pv_win >> 6, (pv_win >> 1) & 31, sBV + (par ^ 1) * 64, old_v[0], old_p[0]);
         }
         float2* sBVw = sBV + (DEFER ? par * 64 : 0);
-#ifdef MPB_EXP_NOREDUCE
-        if (false) {
-#else
         if (q_ok) {
-#endif
             // (row, block) tasks are dealt round-robin to the warps; the refreshed (max, position) pairs
             // only go to shared memory here -- the row warps publish them to bm_val / bm_pos.
             const int ntask = second ? 2 * nvb : nvb;
@@ -1634,7 +1445,7 @@ k_delta(const DeltaArgs a) {
                     float v1 = fmaxf(fmaxf(fmaxf(c10.x, c10.y), fmaxf(c10.z, c10.w)),
                                      fmaxf(fmaxf(c11.x, c11.y), fmaxf(c11.z, c11.w)));
                     if constexpr (MPB_DELTA_FREDUX && NOPOS) {
-                        // NaN operands are ignored by max.f32 / redux.max.f32; a block of NaNs only yields NaN
+                        // NaN operands are ignored by max.f32 / redux.max.f32; only a block of NaNs yields NaN
                         v0 = redux_max_f32(v0) + 0.0f;            // -0 folds into +0, as the key form does
                         v1 = redux_max_f32(v1) + 0.0f;
                     } else {

@@ -13,6 +13,7 @@
 
 #include "../../include/mpb200.h"
 #include "kernels.cuh"
+#include "fused_loop.cuh"
 #include "plan.h"
 
 namespace mpb {
@@ -774,6 +775,11 @@ int mpb200_plan_create(mpb200_plan_t* out, int n_atoms, int atom_size, int n_sam
     MPB_TRY(dev_alloc(p, &p->bm_pos, (size_t)alloc_batch * p->nloc * p->NB));
     MPB_TRY(dev_alloc(p, &p->row_val, (size_t)alloc_batch * p->nloc));
     MPB_TRY(dev_alloc(p, &p->row_pos, (size_t)alloc_batch * p->nloc));
+    if (p->mode == MPB200_MODE_RECORRELATE) {      // fused one-launch loop: ping-pong copy of the row tables, barrier counters
+        MPB_TRY(dev_alloc(p, &p->row_val2, (size_t)alloc_batch * p->nloc));
+        MPB_TRY(dev_alloc(p, &p->row_pos2, (size_t)alloc_batch * p->nloc));
+        MPB_TRY(dev_alloc(p, &p->gbar, (size_t)2));
+    }
     MPB_TRY(dev_alloc(p, &p->residual, (size_t)alloc_batch * n_samples));
     MPB_TRY(dev_alloc(p, &p->best, (size_t)alloc_batch));
     MPB_TRY(dev_alloc(p, &p->fp, (size_t)5));
@@ -985,6 +991,9 @@ int mpb200_plan_set_option(mpb200_plan_t plan, int option, long long value) {
         case MPB200_OPT_FORCE_TABLES:
             p->force_tables = value != 0;
             return MPB200_OK;
+        case MPB200_OPT_FUSED_LOOP:
+            p->fused_loop = value != 0;
+            return MPB200_OK;
         case MPB200_OPT_MAX_STEPS: {
             if (value < 1) return fail(MPB200_EINVAL, "max_steps must be >= 1");
             int rc = check_plan(p, false);
@@ -1077,6 +1086,67 @@ int mpb200_reduce_best(const mpb200_best* cand, int n_ranks, int batch, mpb200_b
     return MPB200_OK;
 }
 
+// The iteration loop of the windowed re-correlation schedule as one cooperative launch (fused_loop.cuh): taken when
+// one CTA per (pair group, signal) is resident at once.  Returns 1 when the shape does not qualify.
+static int pursue_fused(Plan* p, int batch, int n_steps, int32_t* atom_out, int32_t* pos_out, float* val_out,
+                        cudaStream_t st) {
+    if (!p->fused_loop || p->mode != MPB200_MODE_RECORRELATE || p->lcn || n_steps < 2) return 1;
+    if (p->lo != 0 || p->hi != p->K || (p->xconnected && p->xworld > 1)) return 1;
+    int rc = 1;
+    MPB_DISPATCH_M(p->M, {
+        using F = BlockFft<MM, float>;
+        constexpr int TPB = F::T < 256 ? 256 : F::T;
+        constexpr int NT = TPB / F::T;
+        const size_t smem = (size_t)(256 + 2 * NT * F::SMEM_CPX) * sizeof(C32);
+        if (p->fused_occ == 0) {
+            MPB_CUDA(allow_smem(k_pursue_fused<MM>, smem));
+            int coop = 0;
+            MPB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->device));
+            int occ = 0;
+            MPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pursue_fused<MM>, TPB, smem));
+            p->fused_occ = (coop && occ > 0) ? occ : -1;
+        }
+        const long long groups = (p->npairs + NT - 1) / NT;
+        // + 1: a CTA per signal that owns no atom pair -- it records the events and updates the residual
+        if (p->fused_occ > 0 && (groups + 1) * batch <= (long long)p->sm_count * p->fused_occ && batch <= 65535) {
+            if (!p->gbar) return 1;                // (allocated at plan creation in this mode)
+            MPB_CUDA(cudaMemsetAsync(p->gbar, 0, 2 * sizeof(unsigned), st));
+            FusedArgs f;
+            f.pairspec = p->pairspec;
+            f.dict = p->dict;
+            f.residual = p->residual;
+            f.bm_val = p->bm_val;
+            f.bm_pos = p->bm_pos;
+            f.row_val = p->row_val;
+            f.row_pos = p->row_pos;
+            f.row_val2 = p->row_val2;
+            f.row_pos2 = p->row_pos2;
+            f.tw1 = p->tw1;
+            f.tw2 = p->tw2;
+            f.npairs = p->npairs;
+            f.nloc = p->nloc;
+            f.atom_lo = p->lo;
+            f.n_atoms = p->K;
+            f.A = p->A;
+            f.N = p->N;
+            f.NB = p->NB;
+            f.blk_shift = p->blk_shift;
+            f.n_steps = n_steps;
+            f.atom_out = atom_out;
+            f.pos_out = pos_out;
+            f.val_out = val_out;
+            f.gbar = p->gbar;
+            void* kargs[] = {(void*)&f};
+            MPB_CUDA(cudaLaunchCooperativeKernel((const void*)k_pursue_fused<MM>, dim3((unsigned)groups + 1, (unsigned)batch),
+                                                 dim3(TPB), kargs, smem, st));
+            g_launches.fetch_add(1);
+            p->iter += (unsigned)(n_steps - 1);
+            rc = MPB200_OK;
+        }
+    });
+    return rc;
+}
+
 // One resident batch (<= Bcap signals) through begin + n_steps x (apply, refresh).
 static int pursue_resident(Plan* p, const float* signal, int batch, int n_steps, float* residual_out,
                            int32_t* atom_out, int32_t* pos_out, float* val_out, cudaStream_t st) {
@@ -1084,7 +1154,10 @@ static int pursue_resident(Plan* p, const float* signal, int batch, int n_steps,
     int rc = mpb200_begin(reinterpret_cast<mpb200_plan_t>(p), signal, batch, (void*)st);
     if (rc) return rc;
     mark(p, 1, st);
-    for (int s = 0; s < n_steps; ++s) {
+    const int frc = pursue_fused(p, batch, n_steps, atom_out, pos_out, val_out, st);
+    if (frc == MPB200_OK) mark(p, 3, st);
+    else if (frc != 1) return frc;
+    for (int s = 0; frc == 1 && s < n_steps; ++s) {
         const bool last = (s == n_steps - 1);
         rc = launch_apply<true>(p, batch, nullptr, s, n_steps, atom_out, pos_out, val_out,
                                 (!last && p->mode != MPB200_MODE_FULL) ? 1 : 0, st);

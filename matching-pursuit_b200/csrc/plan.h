@@ -53,6 +53,16 @@ struct Plan {
     float* nrow_val = nullptr;      // (Bcap, nloc)
     int* nrow_pos = nullptr;
 
+    // fused iteration loop (windowed re-correlation, latency-bound shapes): one cooperative launch per resident batch
+#ifndef MPB_FUSED_DEFAULT
+#define MPB_FUSED_DEFAULT 1
+#endif
+    bool fused_loop = MPB_FUSED_DEFAULT != 0;   // MPB200_OPT_FUSED_LOOP
+    int fused_occ = 0;              // resident CTAs per SM of k_pursue_fused (0: not queried yet)
+    unsigned* gbar = nullptr;       // [2] grid-barrier counters
+    float* row_val2 = nullptr;      // (Bmax, nloc) second copy of the row maxima (ping-pong across iterations)
+    int* row_pos2 = nullptr;
+
     // Gram mode
     float* gram = nullptr;          // (K, nloc, GS), GS = 2A
     float* map = nullptr;           // (Bmax, nloc, N)

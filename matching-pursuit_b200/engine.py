@@ -107,6 +107,12 @@ class Plan:
         check(self._lib.mpb200_plan_set_option(self._h, 1, int(iterations)), "mpb200_plan_set_option")
         return self
 
+    def set_fused_loop(self, on: bool) -> "Plan":
+        """Windowed re-correlation mode: run the iteration loop of ``sparse_code`` as one cooperative launch when the
+        shape allows it (MPB200_OPT_FUSED_LOOP, default on); off = two launches per iteration."""
+        check(self._lib.mpb200_plan_set_option(self._h, 6, int(bool(on))), "mpb200_plan_set_option")
+        return self
+
     def set_position_free(self, on: bool) -> "Plan":
         """SGRAM mode: force the position-free block tables on or off (chosen automatically otherwise)."""
         check(self._lib.mpb200_plan_set_option(self._h, 4, int(bool(on))), "mpb200_plan_set_option")

@@ -234,6 +234,36 @@ def test_sgram_position_free_tables_equal_exact_positions(case):
         assert np.array_equal(x, y)
 
 
+@pytest.mark.parametrize("case", [(512, 512, 32768, 1, 32), (33, 700, 5000, 3, 30), (64, 128, 4096, 2, 24),
+                                  (16, 2048, 16384, 2, 12), (7, 64, 1500, 4, 9)],
+                         ids=["configs0", "A700_odd_atoms", "A128", "A2048", "tiny"])
+def test_fused_loop_equals_stream_ordered_loop(case):
+    """Windowed re-correlation: the one-launch cooperative loop (k_pursue_fused, MPB200_OPT_FUSED_LOOP, the default
+    when one CTA per (pair group, signal) is resident) must give bit-identical events and residuals to the
+    stream-ordered loop of k_apply + k_corr per iteration, and both must follow the oracle.  A noise signal makes
+    winners at the edges (truncated atoms, windows clipped at 0 and N) common."""
+    k, a, n, b, s = case
+    d = O.make_dictionary(k, a, seed=31)
+    parts = [O.make_planted_signals(d, max(b - 1, 1), n, max(s // 2, 1), seed=32)]
+    if b > 1:
+        parts.append(O.make_noise_signals(1, n, seed=33))
+    sig = torch.cat(parts, dim=0)
+    tr = O.greedy_pursuit(sig, d, s, want_margin=True)
+    outs, launches = {}, {}
+    for on in (False, True):
+        run, plan = plan_runner(d, n, b, "recorrelate")
+        plan.set_fused_loop(on)
+        before = mpb.lib().mpb200_launch_count()
+        outs[on] = run(sig.numpy().reshape(b, n), s)
+        launches[on] = mpb.lib().mpb200_launch_count() - before
+        rep = resync_against_trace(run, sig.numpy(), tr)
+        assert rep.checked == rep.eligible and rep.checked >= 0.9 * rep.total, rep
+        plan.close()
+    for x, y in zip(outs[False], outs[True]):
+        assert np.array_equal(x, y)
+    assert launches[True] < launches[False] - (s - 2), launches     # the fused path was really taken: one launch for the loop
+
+
 def test_sgram_sub_batches_equal_one_batch():
     """A resident-map budget that holds 3 of 7 signals: the batch is walked in balanced sub-batches
     and every signal gets the result it gets alone (signals are independent problems)."""
