@@ -698,6 +698,20 @@ def main():
                                      "nominal (unmeasured) FP32 FMA peak",
                              "achieved_tflops": flops / per_launch_s / 1e12,
                              "nominal_peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12}}
+    elif corr_n and apply_n == 0 and s > 1:
+        # the whole loop ran as ONE cooperative launch per resident batch (k_pursue_fused): latency bound by design --
+        # one grid barrier and a handful of L2 round trips per iteration; the figure that matters is the time per iteration
+        per_launch_s = corr_ms / corr_n / 1e3
+        iters = s - 1                                            # iterations that re-correlate (the last one only subtracts)
+        achieved = alg_bytes * iters / per_launch_s / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_pursue_fused (one cooperative launch per pursuit: winner selection, residual "
+                                              "window transform, spectrum product + inverse FFT, block/row maxima, one grid "
+                                              "barrier per iteration)",
+                    "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "peak_source": peak_src, "traffic": None, "alg_bytes_per_launch": alg_bytes * iters,
+                    "ms_per_launch": corr_ms / corr_n, "us_per_iteration": 1e6 * per_launch_s / iters,
+                    "share_of_step": corr_ms / ev_steps / (ms_total / args.steps),
+                    "note": "latency bound, not bandwidth bound: the fraction is reported for completeness"}
     elif corr_n:
         per_launch_s = corr_ms / corr_n / 1e3
         achieved = alg_bytes / per_launch_s / 1e9
