@@ -264,6 +264,23 @@ def test_fused_loop_equals_stream_ordered_loop(case):
     assert launches[True] < launches[False] - (s - 2), launches     # the fused path was really taken: one launch for the loop
 
 
+def test_fused_loop_falls_back_when_the_grid_does_not_fit():
+    """More (pair group, signal) CTAs than the device holds at once: the option stays on, the stream-ordered loop runs
+    (two launches per iteration) and the results are the oracle's."""
+    k, a, n, b, s = 1024, 128, 2048, 4, 6           # 64 pair groups (+1 writer) x 4 signals > 148 SMs x 1 CTA
+    d = O.make_dictionary(k, a, seed=41)
+    sig = O.make_planted_signals(d, b, n, 4, seed=42)
+    tr = O.greedy_pursuit(sig, d, s, want_margin=True)
+    run, plan = plan_runner(d, n, b, "recorrelate")
+    plan.set_fused_loop(True)
+    before = mpb.lib().mpb200_launch_count()
+    run(sig.numpy().reshape(b, n), s)
+    assert mpb.lib().mpb200_launch_count() - before >= 2 * s - 1
+    rep = resync_against_trace(run, sig.numpy(), tr)
+    assert rep.checked == rep.eligible and rep.checked >= 0.9 * rep.total, rep
+    plan.close()
+
+
 def test_sgram_sub_batches_equal_one_batch():
     """A resident-map budget that holds 3 of 7 signals: the batch is walked in balanced sub-batches
     and every signal gets the result it gets alone (signals are independent problems)."""
