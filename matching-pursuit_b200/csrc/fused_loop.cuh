@@ -47,6 +47,16 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 __device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// Wait until the arrival counter reaches `want`.  The launch is cooperative, so every CTA is resident and the wait is
+// microseconds; a counter that has not moved for 10 s means a broken launch, and the kernel traps (the host sees a
+// launch failure at its next synchronisation) instead of hanging the device.
+__device__ __forceinline__ void wait_counter(const unsigned* p, unsigned want) {
+    if (ld_acquire_u32(p) >= want) return;
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_u32(p) < want) {
+        if (global_ns() - t0 > 10000000000ull) __trap();
+    }
+}
 __device__ __forceinline__ void red_relaxed_add_u32(unsigned* p, unsigned v) {
     asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -173,8 +183,7 @@ k_pursue_fused(const FusedArgs a) {
                 }
                 if (i0 == 0 && !last_step) {             // every worker CTA has read the old window
                     if (threadIdx.x == 0) {
-                        const unsigned want = (unsigned)(s + 1) * nworkers;
-                        while (ld_acquire_u32(a.gbar + 1) < want) {}
+                        wait_counter(a.gbar + 1, (unsigned)(s + 1) * nworkers);
                     }
                     __syncthreads();
                 }
@@ -299,8 +308,7 @@ k_pursue_fused(const FusedArgs a) {
         __syncthreads();
         if (threadIdx.x == 0) {
             red_release_add_u32(a.gbar, 1u);             // release: this CTA's table / residual stores come first
-            const unsigned want = (unsigned)(s + 1) * nctas;
-            while (ld_acquire_u32(a.gbar) < want) {}
+            wait_counter(a.gbar, (unsigned)(s + 1) * nctas);
         }
         __syncthreads();
     }
