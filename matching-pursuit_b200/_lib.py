@@ -23,6 +23,8 @@ MODE_AUTO, MODE_RECORRELATE, MODE_GRAM, MODE_FULL, MODE_SGRAM = 0, 1, 2, 3, 4
 MODES = {"auto": MODE_AUTO, "recorrelate": MODE_RECORRELATE, "gram": MODE_GRAM, "full": MODE_FULL,
          "sgram": MODE_SGRAM}
 MODE_NAMES = {v: k for k, v in MODES.items()}
+# MPB200_OPT_* of include/mpb200.h (tests/test_cabi.py checks the numbers against the header)
+OPT_REFRESH_EVERY, OPT_FORCE_TABLES, OPT_MAX_STEPS, OPT_POSITION_FREE, OPT_LOCAL_CONTRAST_NORM, OPT_FUSED_LOOP = 1, 2, 3, 4, 5, 6
 
 
 class PlanInfo(C.Structure):

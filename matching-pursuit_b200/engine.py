@@ -104,24 +104,24 @@ class Plan:
 
     def set_refresh_every(self, iterations: int) -> "Plan":
         """GRAM mode: re-correlate the whole map every ``iterations`` steps (0 = never)."""
-        check(self._lib.mpb200_plan_set_option(self._h, 1, int(iterations)), "mpb200_plan_set_option")
+        check(self._lib.mpb200_plan_set_option(self._h, _lib.OPT_REFRESH_EVERY, int(iterations)), "mpb200_plan_set_option")
         return self
 
     def set_fused_loop(self, on: bool) -> "Plan":
         """Windowed re-correlation mode: run the iteration loop of ``sparse_code`` as one cooperative launch when the
         shape allows it (MPB200_OPT_FUSED_LOOP, default on); off = two launches per iteration."""
-        check(self._lib.mpb200_plan_set_option(self._h, 6, int(bool(on))), "mpb200_plan_set_option")
+        check(self._lib.mpb200_plan_set_option(self._h, _lib.OPT_FUSED_LOOP, int(bool(on))), "mpb200_plan_set_option")
         return self
 
     def set_position_free(self, on: bool) -> "Plan":
         """SGRAM mode: force the position-free block tables on or off (chosen automatically otherwise)."""
-        check(self._lib.mpb200_plan_set_option(self._h, 4, int(bool(on))), "mpb200_plan_set_option")
+        check(self._lib.mpb200_plan_set_option(self._h, _lib.OPT_POSITION_FREE, int(bool(on))), "mpb200_plan_set_option")
         return self
 
     def set_local_contrast_norm(self, on: bool) -> "Plan":
         """GRAM / SGRAM mode: select on ``fm - avg_pool2d(fm, 9x9)`` incrementally (include/mpb200.h,
         MPB200_OPT_LOCAL_CONTRAST_NORM; modules/matchingpursuit.py:286-296)."""
-        check(self._lib.mpb200_plan_set_option(self._h, 5, int(bool(on))), "mpb200_plan_set_option")
+        check(self._lib.mpb200_plan_set_option(self._h, _lib.OPT_LOCAL_CONTRAST_NORM, int(bool(on))), "mpb200_plan_set_option")
         self.local_contrast_norm = bool(on)
         return self
 

@@ -88,3 +88,18 @@ def test_first_seen_grouping_matches_reference_order():
     perm, seen = mp_mod._first_seen_grouping(atoms)
     assert seen.tolist() == [5, 2, 7, 9]
     assert perm.tolist() == [0, 2, 7, 1, 4, 5, 3, 6]
+
+
+def test_option_and_mode_numbers_match_the_header():
+    """The binding's MPB200_OPT_* / MPB200_MODE_* numbers are the header's."""
+    from matching_pursuit_b200 import _lib
+    text = open(HEADER).read()
+    opts = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+MPB200_OPT_([A-Z_]+)\s+(\d+)", text)}
+    assert opts, "no MPB200_OPT_* in the header"
+    for name, value in opts.items():
+        assert getattr(_lib, "OPT_" + name) == value, name
+    modes = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+MPB200_MODE_([A-Z_]+)\s+(\d+)", text)}
+    for name, value in modes.items():
+        assert getattr(_lib, "MODE_" + name) == value, name
+    version = int(re.search(r"#define\s+MPB200_VERSION\s+(\d+)", text).group(1))
+    assert _lib.ABI_VERSION == version
