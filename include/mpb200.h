@@ -100,7 +100,7 @@ int mpb200_plan_info_get(mpb200_plan_t plan, mpb200_plan_info* info);
 /* MPB200_OPT_POSITION_FREE (SGRAM mode, blocks of >= 128 positions): 1 = the block/row maxima tables carry block
  * starts instead of exact positions and the kernel that applies a winner resolves its exact position from the
  * resident map; 0 = exact positions everywhere.  Chosen automatically at plan creation (on when the refresh kernel
- * dominates: >= 16384 (atom pair, signal) work items per iteration); results are identical either way.  Takes
+ * dominates: >= 1024 (atom pair, signal) work items per iteration); results are identical either way.  Takes
  * effect from the next mpb200_begin / mpb200_sparse_code. */
 #define MPB200_OPT_POSITION_FREE 4
 /* MPB200_OPT_LOCAL_CONTRAST_NORM (GRAM / SGRAM mode, un-sharded plans): 1 = the selection of mpb200_sparse_code runs
