@@ -1117,6 +1117,13 @@ struct DeltaArgs {
 #ifndef MPB_DELTA_TRIMST
 #define MPB_DELTA_TRIMST 1     // only the updated range of the staged rows is stored back (16-byte granules)
 #endif
+#ifndef MPB_DELTA_DB
+#define MPB_DELTA_DB 1         // 4096-point transforms only: TWO CTAs per SM with 128 registers -- the pair spectrum stays in
+                               // registers for the run of items that share it (no 32 KB L2 read per item) -- and a
+                               // DOUBLE-BUFFERED map window: the next item's window is requested right after this item's
+                               // stores are issued, into the other buffer, so neither the store drain nor the HBM latency
+                               // of the window sits between two items of a CTA
+#endif
 #ifndef MPB_DELTA_E
 #define MPB_DELTA_E 0          // complex values per thread of k_delta's transform (0: BlockFft's default, 16 up to 4096 points)
 #endif
@@ -1132,21 +1139,28 @@ constexpr int delta_elems(int m2, int want) {      // `want` values per thread i
                                // two).  Correct (parity suite green) but measured 8.78 against 8.71 ms per 256 signals:
                                // the warps wait at the remaining barrier instead.  Kept as a measured variant.
 #endif
-template <int M2>
+#ifndef MPB_DELTA_DB_MIN_BATCH
+#define MPB_DELTA_DB_MIN_BATCH 32   // resident signals from which the host launches the DB form (the run of items per
+                                    // pair spectrum is the batch; one signal of 8192 items: 204 us without, 238 us with)
+#endif
+template <int M2, bool DBT = false>
 struct DeltaCfg {
     using F = BlockFft<M2, float, delta_elems(M2, MPB_DELTA_E)>;
     static constexpr int TPB = F::T < MPB_DELTA_TPB ? MPB_DELTA_TPB : F::T;
     // the spectra tables are stored in that form's order, so producers and consumer must agree (plan build vs k_delta)
     static constexpr bool LOCAL = MPB_DELTA_LOCAL && MPB_DELTA_SPREF && F::HAS_LOCAL && F::T == 256;
+    static constexpr bool DB = DBT && MPB_DELTA_DB && MPB_DELTA_SPREF && !LOCAL && M2 == 4096 && TPB == F::T;
+    static constexpr int MINB = DB ? 2 : MPB_DELTA_MINB;
+    static constexpr int NSTAGE = DB ? 2 : 1;          // staging buffers (of two rows) per transform
 };
 // NOPOS: the block and row tables carry no exact positions -- a candidate's "position" is the start of its block
 // (blocks order like positions, so ties resolve alike) and k_apply finds the first position of the maximum inside
 // that block of the resident map.  Saves the position half of every block reduction (whole blocks of 128/256).
-template <int M2, bool NOPOS>
-__global__ void __launch_bounds__(DeltaCfg<M2>::TPB, MPB_DELTA_MINB)
+template <int M2, bool NOPOS, bool DBT = false>
+__global__ void __launch_bounds__((DeltaCfg<M2, DBT>::TPB), (DeltaCfg<M2, DBT>::MINB))
 k_delta(const DeltaArgs a) {
-    using F = typename DeltaCfg<M2>::F;
-    constexpr int TPB = DeltaCfg<M2>::TPB;
+    using F = typename DeltaCfg<M2, DBT>::F;
+    constexpr int TPB = DeltaCfg<M2, DBT>::TPB;
     constexpr int NT = TPB / F::T;
     constexpr int NW = F::T / 32;
     constexpr int RW0 = NW >= 4 ? NW - 2 : 0;            // first of the warps that re-derive the row maxima
@@ -1155,7 +1169,10 @@ k_delta(const DeltaArgs a) {
     C32* stw2 = reinterpret_cast<C32*>(smraw);
     const int sb = threadIdx.x / F::T, tl = threadIdx.x % F::T;
     C32* sm = stw2 + 256 + (size_t)sb * F::SMEM_CPX;
-    float* st0 = reinterpret_cast<float*>(stw2 + 256 + (size_t)NT * F::SMEM_CPX) + (size_t)sb * 2 * a.cap;
+    constexpr bool DB = DeltaCfg<M2, DBT>::DB;
+    float* const stage = reinterpret_cast<float*>(stw2 + 256 + (size_t)NT * F::SMEM_CPX) +
+                         (size_t)sb * 2 * DeltaCfg<M2, DBT>::NSTAGE * a.cap;
+    float* st0 = stage;                                  // DB: re-aimed at the item's buffer at every item top
     float* st1 = st0 + a.cap;
     constexpr bool DEFER = MPB_DELTA_DEFER && NW == 8;   // needs dedicated row warps (M2 >= 4096)
     constexpr bool LOCAL = DeltaCfg<M2>::LOCAL;
@@ -1234,9 +1251,30 @@ k_delta(const DeltaArgs a) {
             a.row_pos[rowi] = (at == INT_MAX) ? 0 : at;
         }
     };
+    // DB: tl == 0 requests the map window of item (pair qq, signal bb, winner position pos) into staging buffer `which_buf`
+    auto request_window_into = [&](int qq, int bb, int pos, int which_buf) {
+        const int wfirst = max(0, pos - a.A + 1), wlast = pos + a.A - 1;
+        const int wblk0 = wfirst >> a.blk_shift, wnvb = (wlast >> a.blk_shift) - wblk0 + 1;
+        const int wstart = wblk0 << a.blk_shift;
+        const unsigned bytes = (unsigned)min(wnvb << a.blk_shift, a.NS - wstart) * 4u;
+        const float* w0 = a.map + ((size_t)bb * a.nloc + 2 * qq) * a.NS + wstart;
+        float* dst = stage + (size_t)which_buf * 2 * a.cap;
+        const bool wsecond = 2 * qq + 1 < a.nloc;
+        mbar_expect_tx(bar, wsecond ? 2u * bytes : bytes);
+        bulk_load(dst, w0, bytes, bar);
+        if (wsecond) bulk_load(dst + a.cap, w0 + a.NS, bytes, bar);
+    };
+    int wpar = 0;                                        // DB: staging buffer of the current item
+    bool win_pre = false;                                // DB, tl == 0: the current item's window was requested by the previous one
+    int eq_q = -1;                                       // DB: the pair whose spectrum eqr[] holds
+    C32 eqr[DB ? F::E : 1];
     for (; n_items > 0; --n_items, b = (b + 1 == a.batch ? 0 : b + 1), g += (b == 0)) {
         const GramUpdate u = a.upd[b];
         const int b_next = (b + 1 == a.batch ? 0 : b + 1);
+        if constexpr (DB) {
+            st0 = stage + (size_t)wpar * 2 * a.cap;
+            st1 = st0 + a.cap;
+        }
         if (!u.valid) {                                  // CTA-uniform: this signal takes the FFT route
             if (MPB_DELTA_SPREF && tl == 0 && n_items > 1) request_spectrum(b_next);   // nobody touches the buffer now
             continue;
@@ -1269,7 +1307,8 @@ k_delta(const DeltaArgs a) {
                     while (!mbar_try_wait(barF, phaseF)) {}
                     phaseF ^= 1u;
                 }
-                if (q_ok) request_window();
+                if (q_ok && !(DB && win_pre)) request_window();
+                win_pre = false;
             }
         } else if (tl == 0 && q_ok) request_window();
         // the old row maxima are fetched now so that the row phase never waits on memory (DEFER: those of the
@@ -1302,16 +1341,28 @@ k_delta(const DeltaArgs a) {
                 // the pair spectrum comes from L2 while the winner spectrum -- requested during the previous item's
                 // reduction phase -- is read from this thread's own slots of the FFT buffer (the slots pass 1
                 // overwrites below: no barrier needed)
+                if constexpr (DB) {
+                    if (eq_q != q) {                     // a CTA walks the whole batch per pair group: once per ~batch items
 #pragma unroll
-                for (int e = 0; e < F::E; ++e) {
-                    const float2 y = __ldg(reinterpret_cast<const float2*>(Eq + F::in_index(tl, e)));
-                    r[e] = C32{y.x, y.y};
+                        for (int e = 0; e < F::E; ++e) {
+                            const float2 y = __ldg(reinterpret_cast<const float2*>(Eq + F::in_index(tl, e)));
+                            eqr[e] = C32{y.x, y.y};
+                        }
+                        eq_q = q;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < F::E; ++e) {
+                        const float2 y = __ldg(reinterpret_cast<const float2*>(Eq + F::in_index(tl, e)));
+                        r[e] = C32{y.x, y.y};
+                    }
                 }
                 while (!mbar_try_wait(barS, phaseS)) {}
                 phaseS ^= 1u;
 #pragma unroll
                 for (int e = 0; e < F::E; ++e) {
-                    if constexpr (LOCAL) r[e] = cmul(sm[F::slot_addr_local(tl, e)], r[e]);
+                    if constexpr (DB) r[e] = cmul(sm[F::slot_addr(tl, e)], eqr[e]);
+                    else if constexpr (LOCAL) r[e] = cmul(sm[F::slot_addr_local(tl, e)], r[e]);
                     else r[e] = cmul(sm[F::slot_addr(tl, e)], r[e]);
                 }
             } else {
@@ -1408,6 +1459,20 @@ k_delta(const DeltaArgs a) {
                 if (second) bulk_store(m1, st1, (unsigned)cnt * 4u);
             }
             bulk_commit();
+        }
+        if constexpr (DB) {
+            // the NEXT item's window goes into the other staging buffer now: its last reader was the block reduction
+            // of the previous item (every warp has passed three barriers since) and the bulk store of the previous
+            // item, which `wait_group.read 1` -- all but the group just committed -- has seen leave
+            if (tl == 0 && n_items > 1) {
+                const GramUpdate un = a.upd[b_next];
+                const int qn = (g + (b_next == 0 ? 1 : 0)) * NT + sb;
+                if (un.valid && qn < a.npairs) {
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    request_window_into(qn, b_next, un.position, wpar ^ 1);
+                    win_pre = true;
+                }
+            }
         }
         if (MPB_DELTA_SPREF && tl == 0 && n_items > 1) request_spectrum(b_next);
         if constexpr (DEFER) {
@@ -1545,6 +1610,7 @@ k_delta(const DeltaArgs a) {
             pv_row = q_ok ? (int)((size_t)b * a.nloc + 2 * q) : -1;
             pv_win = (blk0 << 6) | (nvb << 1) | (second ? 1 : 0);
             par ^= 1;
+            if constexpr (DB) wpar ^= 1;
         } else {
             __syncthreads();   // block maxima staged; nobody reads the staging rows any more
 #pragma unroll

@@ -429,18 +429,24 @@ static int step_refresh_raw(Plan* p, int batch, cudaStream_t st) {
                 using F = typename DeltaCfg<MM>::F;
                 constexpr int TPB = DeltaCfg<MM>::TPB;
                 constexpr int NT = TPB / F::T;
+                // the double-buffered two-CTA form pays when a CTA meets the same pair spectrum for many items in a row
+                const bool db = DeltaCfg<MM, true>::DB && batch >= MPB_DELTA_DB_MIN_BATCH;
                 const size_t smem = (size_t)(256 + NT * F::SMEM_CPX) * sizeof(C32) +
-                                    (size_t)NT * 2 * d.cap * sizeof(float);
-                auto kernel = p->pos_free ? k_delta<MM, true> : k_delta<MM, false>;
+                                    (size_t)NT * 2 * (db ? 2 : 1) * d.cap * sizeof(float);
+                void (*kernel)(DeltaArgs) = p->pos_free ? k_delta<MM, true, false> : k_delta<MM, false, false>;
+                if constexpr (DeltaCfg<MM, true>::DB) {
+                    if (db) kernel = p->pos_free ? k_delta<MM, true, true> : k_delta<MM, false, true>;
+                }
                 MPB_CUDA(allow_smem(kernel, smem));
-                if (p->delta_occ == 0) {
-                    MPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->delta_occ, kernel, TPB, smem));
-                    if (p->delta_occ < 1) p->delta_occ = 1;
+                int& occ = db ? p->delta_occ_db : p->delta_occ;
+                if (occ == 0) {
+                    MPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, TPB, smem));
+                    if (occ < 1) occ = 1;
                 }
                 d.ngroups = (p->npairs + NT - 1) / NT;
                 const long long items = (long long)d.ngroups * batch;
                 if (items >= (1LL << 31)) return fail(MPB200_EINVAL, "SGRAM: more than 2^31 (pair, signal) work items per launch");
-                long long ctas = (long long)p->sm_count * p->delta_occ;
+                long long ctas = (long long)p->sm_count * occ;
                 if (ctas > items) ctas = items;
                 MPB_CUDA(launch_pdl(kernel, dim3((unsigned)ctas), dim3(TPB), smem, st, d));
             });
@@ -577,7 +583,10 @@ static int preload_kernels(Plan* p) {
         touch(k_corr<MM, MODE_DENSE | MODE_BLOCKMAX | MODE_ROWMAX>);
     });
     if (p->mode == MPB200_MODE_SGRAM) {
-        MPB_DISPATCH_M(p->M2, { touch(k_delta<MM, true>); touch(k_delta<MM, false>); touch(k_window_fft<MM, 1>); touch(k_window_fft<MM, 2>); });
+        MPB_DISPATCH_M(p->M2, {
+            touch(k_delta<MM, true>); touch(k_delta<MM, false>); touch(k_window_fft<MM, 1>); touch(k_window_fft<MM, 2>);
+            if constexpr (DeltaCfg<MM, true>::DB) { touch(k_delta<MM, true, true>); touch(k_delta<MM, false, true>); }
+        });
     }
     touch(k_gram_update<16>);
     touch(k_gram_update<32>);
@@ -963,7 +972,7 @@ int mpb200_plan_set_option(mpb200_plan_t plan, int option, long long value) {
             if (p->mode != MPB200_MODE_SGRAM) return fail(MPB200_EINVAL, "position-free tables exist in SGRAM mode only");
             if (value != 0 && p->blk < 128) return fail(MPB200_EINVAL, "position-free tables need blocks of >= 128 positions");
             p->pos_free = value != 0;
-            p->delta_occ = 0;          // another kernel instantiation: re-query its occupancy
+            p->delta_occ = p->delta_occ_db = 0;          // another kernel instantiation: re-query its occupancy
             p->cur_batch = 0;          // tables of a batch in flight were built under the other convention
             return MPB200_OK;
         case MPB200_OPT_LOCAL_CONTRAST_NORM: {
@@ -984,7 +993,7 @@ int mpb200_plan_set_option(mpb200_plan_t plan, int option, long long value) {
             }
             p->lcn = true;
             p->pos_free = false;       // the normalised tables carry exact positions
-            p->delta_occ = 0;
+            p->delta_occ = p->delta_occ_db = 0;
             p->cur_batch = 0;
             return MPB200_OK;
         }

@@ -19,6 +19,7 @@ struct Plan {
     int Bcap = 0;                                   // signals resident at once (<= Bmax; map modes sub-batch)
     int NS = 0;                                     // row stride of the resident map (N, or N padded to 4 in SGRAM)
     int delta_occ = 0;                              // SGRAM: resident CTAs per SM of k_delta (persistent grid)
+    int delta_occ_db = 0;                           // ... of its double-buffered two-CTA form (large resident batches)
     int M2 = 0;                                     // SGRAM: transform length of the synthesised Gram rows (>= 2A)
     bool pos_free = false;                          // SGRAM with blocks of >= 128 positions: the block/row tables carry block
                                                     // starts instead of exact positions (k_delta NOPOS); k_apply resolves
