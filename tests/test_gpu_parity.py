@@ -281,6 +281,26 @@ def test_fused_loop_falls_back_when_the_grid_does_not_fit():
     plan.close()
 
 
+def test_sgram_two_cta_form_equals_three_cta_form_and_oracle():
+    """k_delta's double-buffered two-CTA form (4096-point transforms, resident batches of >= 32 signals: pair spectrum
+    in registers, next window prefetched into the second staging buffer) against the three-CTA form the same plan takes
+    for a batch of 16 -- bit-identical events and residuals -- and against the oracle.  Noise signals make winners at
+    both edges (windows clipped at 0, truncated atoms that take the FFT route and break the prefetch chain) common."""
+    k, a, n, b, s = 10, 2048, 8192, 32, 10
+    d = O.make_dictionary(k, a, seed=51)
+    sig = torch.cat([O.make_planted_signals(d, b - 4, n, 5, seed=52), O.make_noise_signals(4, n, seed=53)], dim=0)
+    tr = O.greedy_pursuit(sig, d, s, want_margin=True)
+    run, plan = plan_runner(d, n, b, "sgram")
+    assert plan.fft_size2 == 4096
+    whole = run(sig.numpy().reshape(b, n), s)                       # one launch per iteration over 32 signals
+    halves = [run(sig.numpy().reshape(b, n)[i:i + 16], s) for i in (0, 16)]
+    for j, x in enumerate(whole):
+        assert np.array_equal(x, np.concatenate([h[j] for h in halves], axis=0))
+    rep = resync_against_trace(run, sig.numpy(), tr)
+    assert rep.checked == rep.eligible and rep.checked >= 0.9 * rep.total, rep
+    plan.close()
+
+
 def test_sgram_sub_batches_equal_one_batch():
     """A resident-map budget that holds 3 of 7 signals: the batch is walked in balanced sub-batches
     and every signal gets the result it gets alone (signals are independent problems)."""
